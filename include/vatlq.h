@@ -1,0 +1,168 @@
+/*
+ * vatlq.h — C ABI of libvatlq.so, the B200 (sm_100a) implementation of VATL4Pose's
+ * active-learning query pass.
+ *
+ * The reference (ImIntheMiddle/VATL4Pose-WACV2024) has no FFI for this path: the boundary
+ * is Python (`ActiveLearning.eval_and_query`, active_learning/ActiveLearning.py:253-649).
+ * Each entry point below names the reference function whose arithmetic it replaces; the
+ * Python host layer (vatl4pose-wacv2024_b200/) binds these with ctypes and mirrors the
+ * reference's callables.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED device pointer (torch.Tensor.data_ptr()) unless the
+ *     parameter name starts with `host_`; the library never frees caller memory.
+ *   - scratch comes from the caller: query `*_workspace_bytes()` and pass `ws`.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except the
+ *     ones documented as synchronising.
+ *   - return 0 on success, a cudaError_t (>0) or a negative VATLQ_E* code otherwise;
+ *     `vatlq_last_error()` returns a thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VATLQ_H
+#define VATLQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VATLQ_ABI_VERSION 1
+
+#define VATLQ_EINVAL (-1)  /* bad argument (shape, alignment, null pointer)        */
+#define VATLQ_ENOMEM (-2)  /* workspace too small                                  */
+#define VATLQ_ECOMM (-3)   /* NCCL missing or a collective failed                  */
+#define VATLQ_ESTATE (-4)  /* internal invariant violated (reported, never hidden) */
+
+typedef void* vatlq_stream_t; /* cudaStream_t */
+
+int vatlq_abi_version(void);
+const char* vatlq_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t vatlq_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Heat-map scan: THC + local-peak statistics + argmax / quarter-pixel coordinates.
+ * Replaces, for a whole id-sorted pool at once,
+ *   ActiveLearning.compute_thc            active_learning/ActiveLearning.py:747-760
+ *   its call-site logic (x2 rule)         active_learning/ActiveLearning.py:345-363
+ *   localpeak_values / localpeak_mean     active_learning/local_peak.py:5-22
+ *   heatmap_to_coord_simple/get_max_pred  alphapose/utils/transforms.py:550-583,710-727
+ *   transform_preds/get_affine_transform  alphapose/utils/transforms.py:704-708,753-792
+ *
+ * H          (n,J,h,w) fp32 contiguous heat maps; every frame is read from HBM once.
+ * is_prev/is_next  u8[n] track-adjacency flags (alphapose/datasets/posetrack21.py:148-178);
+ *            the t-1 / t+1 maps are H[t-1] / H[t+1].
+ * halo_prev/halo_next  optional (J,h,w) frames that precede H[0] / follow H[n-1] when the
+ *            pool is a shard or a chunk of a longer pool (NULL: no such neighbour).
+ * bbox_xyxy  optional fp32[n,4] crop boxes; required for kpts.
+ * Outputs (any may be NULL to skip):
+ *   thc[n]        fp32  temporal heat-map continuity
+ *   peak_sum[n], peak_cnt[n], peak_mean[n]  kept-peak sum / count / mean (NaN when count 0)
+ *   coords_hm[n,J,2]  fp32 heat-map-space (x,y) incl. the +-0.25 shift  (bit-exact)
+ *   kpts[n,J,3]   fp32 image-space x, y and peak value == the reference's `keypoints` row
+ *                 (ActiveLearning.py:306-307)
+ * ------------------------------------------------------------------------------------ */
+size_t vatlq_heatmap_scan_workspace_bytes(int64_t n, int J);
+int vatlq_heatmap_scan(const float* H, const uint8_t* is_prev, const uint8_t* is_next,
+                       int64_t n, int J, int h, int w,
+                       const float* halo_prev, const float* halo_next,
+                       const float* bbox_xyxy,
+                       float* thc, float* peak_sum, int32_t* peak_cnt, float* peak_mean,
+                       float* coords_hm, float* kpts,
+                       void* ws, size_t ws_bytes, vatlq_stream_t stream);
+
+/* Strict three-tensor THC (cur, prev, next separately forwarded as the reference does,
+ * ActiveLearning.py:293-297,345-363).  prev/next may be NULL when no flag needs them. */
+int vatlq_thc3(const float* cur, const float* prev, const float* next,
+               const uint8_t* is_prev, const uint8_t* is_next,
+               int64_t n, int J, int h, int w, float* thc, vatlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * WPU: hybrid feature + whole-body auto-encoder + reconstruction MSE.  Replaces
+ *   bbox_xyxy_to_xywh    alphapose/utils/bbox.py:91-97
+ *   compute_hybrid       active_learning/Whole_body_AE/hybrid_feature.py:14-58 (fp64)
+ *   WholeBodyAE.forward  active_learning/Whole_body_AE/AutoEncoder.py:13-39   (fp32)
+ *   MSELoss call sites   active_learning/ActiveLearning.py:364-370 (all dims) and
+ *                        :371-386 (drop_ears: dims 3,4,20,21 removed)
+ * kpts[n,17,3] fp32 (x,y,score), bbox_xyxy[n,4] fp32 crop boxes.
+ * weights: the 8 Linear layers packed back to back, each W[out][in] row-major then b[out],
+ *          dims in_dim->24->12->7->z_dim->7->12->24->in_dim (in_dim must be 42).
+ * wpu[n] fp32; feat (optional) fp32[n,in_dim] = the `.float()` feature fed to the AE;
+ * status[n] u8: 0 ok, 1 height<=0, 2 sum(scores)<=0 (the reference's AssertionErrors,
+ * hybrid_feature.py:25,31); wpu is NaN for those rows.
+ * ------------------------------------------------------------------------------------ */
+size_t vatlq_wpu_weight_count(int in_dim, int z_dim);
+int vatlq_wpu(const float* kpts, const float* bbox_xyxy, const float* weights,
+              int in_dim, int z_dim, int drop_ears,
+              float* wpu, float* feat, uint8_t* status, int64_t n, vatlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Score fusion (active_learning/ActiveLearning.py:490-516) in float64 on the device.
+ * Three steps so that a multi-GPU caller can all-reduce the 4 / 2 statistics in between:
+ *   stats1[4] = {min thc, -max thc, min wpu, -max wpu} over rows with unlabeled[i]!=0
+ *   combine   : u_i = combine(minmax(thc_i), minmax(wpu_i)); stats2[2] = {min u, -max u}
+ *   final     : unc_i = minmax(u_i) for unlabelled rows, 0 for labelled rows
+ * (all statistics are stored "min of value / min of negated value" so one MIN all-reduce
+ * serves).  mode: 0 const (a+b), 1 increase, 2 decrease, 3 single criterion (wpu ignored).
+ * ------------------------------------------------------------------------------------ */
+int vatlq_fuse_stats(const float* thc, const float* wpu, const uint8_t* unlabeled, int64_t n,
+                     double* stats1, vatlq_stream_t stream);
+int vatlq_fuse_combine(const float* thc, const float* wpu, const uint8_t* unlabeled, int64_t n,
+                       const double* stats1, int mode, double labeled_ratio,
+                       double* u, double* stats2, vatlq_stream_t stream);
+int vatlq_fuse_final(const uint8_t* unlabeled, int64_t n, const double* stats2,
+                     double* u_inout, vatlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * k-center greedy core-set (ActiveLearning.coreset_selection,
+ * active_learning/ActiveLearning.py:798-850; sklearn euclidean pairwise_distances in fp64).
+ *
+ * X[n,d] fp32 row-major (the reference holds the same values as float64, :270,286); all
+ * distance arithmetic accumulates in fp64.  d must be a multiple of 4, X 16-byte aligned.
+ * The handle owns nothing but small control blocks inside `ws`.
+ *
+ * Multi-GPU: X is replicated, rows [row_lo,row_hi) are owned by this rank; min_d / unc are
+ * full-length arrays of which only the owned slice is maintained.  comm is a handle from
+ * vatlq_comm_init (NULL for one GPU).
+ *
+ *   rule: 0 w_unc       argmax((1-moks)*min_d + (lambda*moks)*unc)   (:815-821)
+ *         1 fixed       argmax(min_d + lambda*unc)                   (:822-827)
+ *         2 dist        argmax(min_d); first pick given by caller    (:828-833)
+ *   n_labeled == 0: the first pick is argmax(unc) (rule 0/1) or `first_pick` (rule 2).
+ *   batch: 1 = one pick per pass over X (GEMV form); >1 = up to `batch` picks per pass,
+ *          decided exactly in advance on a candidate set.
+ * out_idx[k] int64 picks in order (device).  min_d[n] fp64 in/out (initialised by
+ * vatlq_coreset_init), unc[n] fp64 in/out (picked entries zeroed like :848).
+ * host_stats (optional, 8 x int64, host memory, written at the end — the call then
+ * synchronises): passes over X, picks, fallback picks, candidate overflow events, ...
+ * ------------------------------------------------------------------------------------ */
+size_t vatlq_coreset_workspace_bytes(int64_t n, int d, int batch);
+int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
+                       const int64_t* labeled, int64_t n_labeled,
+                       double* min_d, void* ws, size_t ws_bytes, vatlq_stream_t stream);
+int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
+                         double* min_d, double* unc,
+                         int rule, double moks, double lambda, int64_t n_labeled,
+                         int64_t first_pick, int64_t k, int batch,
+                         int64_t* out_idx, void* comm,
+                         void* ws, size_t ws_bytes, int64_t* host_stats, vatlq_stream_t stream);
+
+/* One pairwise-distance column block, exposed for parity tests of the distance arithmetic:
+ * out[i*m + j] = d(X[i], X[centers[j]]) in fp64 (sklearn _euclidean_distances order). */
+int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
+                        double* out, vatlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * NCCL plumbing for the multi-GPU argmax exchange (one process per GPU).  NCCL is
+ * dlopen()ed (libnccl.so.2, the copy torch already loaded); absent -> VATLQ_ECOMM.
+ * ------------------------------------------------------------------------------------ */
+int vatlq_comm_unique_id(void* host_id128);                 /* rank 0: 128-byte id       */
+int vatlq_comm_init(const void* host_id128, int rank, int world, void** comm_out);
+int vatlq_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VATLQ_H */

@@ -1,0 +1,56 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Build libvatlq.so if needed (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+    g.build()
+    import vatlq
+    return vatlq
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def gold_scan():
+    return load_golden("scan.npz")
+
+
+@pytest.fixture(scope="session")
+def gold_wpu():
+    return load_golden("wpu.npz")
+
+
+@pytest.fixture(scope="session")
+def gold_fuse():
+    return load_golden("fuse.npz")
+
+
+@pytest.fixture(scope="session")
+def gold_coreset():
+    z = load_golden("coreset.npz")
+    cases = {}
+    for key in z.files:
+        tag, field = key.split("/")
+        cases.setdefault(tag, {})[field] = z[key]
+    return cases
+
+
+def ae_weights_from_gold(z):
+    return [(z[f"W{k}"], z[f"b{k}"]) for k in range(8)]

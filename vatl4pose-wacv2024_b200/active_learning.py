@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's query interface (active_learning/ActiveLearning.py).
+
+Same names, argument meaning and error behaviour as the reference for the ONE path this
+package accelerates — `ActiveLearning.eval_and_query()` and the helper callables it uses —
+with the per-person Python loop replaced by batched CUDA kernels (ops.py / libvatlq.so).
+Everything else of the reference class (dataset building, estimator training, mAP/OSPA
+evaluation, plotting) is out of scope and is injected or hooked:
+
+    al = ActiveLearning(cfg, opt, model=estimator, eval_loader=loader, eval_len=len(dataset), AE=ae)
+    al.eval_and_query()          # fills labeled_id / unlabeled_id / query_list_list / ...
+    al.outcome()                 # bookkeeping of :166-205 without the retraining
+
+Strategy names are the reference's (`opt.uncertainty`, `opt.representativeness`, `opt.filter`,
+ActiveLearning.py:329-401,467-481,533-619).  THC*, WPU*, THC+WPU and None with filter None or
+Coreset run here; any other name raises NotImplementedError naming the reference code path to
+use (dispatch to the reference, never a CPU re-implementation of ours).
+"""
+from __future__ import annotations
+
+import copy
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .query import QueryPass
+
+__all__ = ["ActiveLearning", "IndexCollection", "WholeBodyAE", "compute_thc", "localpeak_mean",
+           "heatmap_to_coord_simple", "compute_hybrid", "coreset_selection"]
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.VatlqError("no CUDA device: the query pass has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_cuda(a, dtype=torch.float32):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=_dev(), dtype=dtype).contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# single-item shims with the reference's signatures (tests read like the reference's code)
+# ----------------------------------------------------------------------------------------
+
+def compute_thc(heatmaps, heatmaps_adj, norm_type="L1"):
+    """ActiveLearning.compute_thc (ActiveLearning.py:747-760) for one pair of (J,H,W) stacks."""
+    if norm_type != "L1":
+        raise NotImplementedError("only the L1 norm is on the query path (ActiveLearning.py:346)")
+    cur = _as_cuda(heatmaps)[None]
+    adj = _as_cuda(heatmaps_adj)[None]
+    one = torch.ones(1, dtype=torch.uint8)
+    # a single existing neighbour is doubled at the call site (:355-362), not in compute_thc
+    return float(ops.thc3(cur, adj, None, one, 1 - one)[0]) / 2.0
+
+
+def localpeak_mean(heatmaps, filter_size=3, order=0.5):
+    """active_learning/local_peak.py:12-22 for one (J,H,W) stack."""
+    if filter_size != 3 or order != 0.5:
+        raise NotImplementedError("the query path uses filter_size=3, order=0.5 (ActiveLearning.py:412)")
+    return float(ops.heatmap_scan(_as_cuda(heatmaps)[None]).peak_mean[0])
+
+
+def heatmap_to_coord_simple(hms, bbox, hms_flip=None, **kwargs):
+    """alphapose/utils/transforms.py:550-583 for one (J,H,W) stack -> (preds (J,2), maxvals (J,1))."""
+    h = _as_cuda(hms)
+    if hms_flip is not None:
+        h = (h + _as_cuda(hms_flip)) / 2
+    box = torch.tensor([list(map(float, bbox))], dtype=torch.float32)
+    r = ops.heatmap_scan(h[None], boxes_xyxy=box)
+    k = r.kpts[0].cpu().numpy()
+    return k[:, :2].copy(), k[:, 2:3].copy()
+
+
+def compute_hybrid(bbox, keypoints):
+    """active_learning/Whole_body_AE/hybrid_feature.py:14-58.  bbox is [x,y,w,h]; returns the
+    42-d feature as float64 holding the float32 values the auto-encoder is fed (`.float()`,
+    ActiveLearning.py:367)."""
+    k = np.asarray(keypoints, dtype=np.float32).reshape(1, ops.J, 3)
+    x, y, w, h = [float(v) for v in bbox]
+    box = torch.tensor([[x, y, x + w - 1, y + h - 1]], dtype=torch.float32)   # inverse of bbox.py:95-97
+    dummy = torch.zeros(int(_lib.lib().vatlq_wpu_weight_count(42, 4)), device=_dev())
+    _, feat = ops.wpu(_as_cuda(k), box, dummy, 42, 4, return_features=True)
+    return feat[0].double().cpu().numpy()
+
+
+class WholeBodyAE(nn.Module):
+    """Layer stack of active_learning/Whole_body_AE/AutoEncoder.py:5-39.  The reference hard-codes
+    input_dim=38 while its call site feeds 42 features; here the width is an
+    argument defaulting to what compute_hybrid emits.  `forward` is plain torch (used for
+    training, which stays reference code); `unnaturalness` is the fused CUDA scoring path."""
+
+    def __init__(self, z_dim=2, kp_direct=False, input_dim=42):
+        super().__init__()
+        if kp_direct:
+            raise NotImplementedError("kp_direct auto-encoders are not on the query path")
+        self.z_dim, self.input_dim = z_dim, input_dim
+        self.encoder = nn.Sequential(nn.Linear(input_dim, 24), nn.ReLU(True), nn.Linear(24, 12), nn.ReLU(True),
+                                     nn.Linear(12, 7), nn.ReLU(True), nn.Linear(7, z_dim))
+        self.decoder = nn.Sequential(nn.Linear(z_dim, 7), nn.ReLU(True), nn.Linear(7, 12), nn.ReLU(True),
+                                     nn.Linear(12, 24), nn.ReLU(True), nn.Linear(24, input_dim), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.decoder(self.encoder(x))
+
+    def unnaturalness(self, kpts, boxes_xyxy, drop_ears=False):
+        w, ind, z = ops.pack_ae_weights(self, _dev())
+        return ops.wpu(_as_cuda(kpts).reshape(-1, ops.J, 3), _as_cuda(boxes_xyxy).reshape(-1, 4), w, ind, z, drop_ears)
+
+
+class IndexCollection:
+    """The part of alipy.index.IndexCollection (ALiPy/alipy/index/index_collections.py:26-226)
+    the query path uses: an ordered, duplicate-free list of ints with set-speed membership."""
+
+    def __init__(self, data=None):
+        self._list, self._set = [], set()
+        if data is not None:
+            self.update(data)
+
+    @property
+    def index(self):
+        return list(self._list)   # the reference hands out a copy (:91-95)
+
+    def __len__(self):
+        return len(self._list)
+
+    def __contains__(self, v):
+        return int(v) in self._set
+
+    def __iter__(self):
+        return iter(self._list)
+
+    def add(self, v):
+        v = int(v)
+        if v not in self._set:
+            self._set.add(v)
+            self._list.append(v)
+        return self
+
+    def discard(self, v):
+        v = int(v)
+        if v in self._set:
+            self._set.remove(v)
+            self._list.remove(v)
+        return self
+
+    def update(self, other):
+        for v in other:
+            self.add(v)
+        return self
+
+    def difference_update(self, other):
+        drop = {int(v) for v in other} & self._set
+        if drop:
+            self._set -= drop
+            self._list = [v for v in self._list if v not in drop]
+        return self
+
+
+def coreset_selection(self, embeddings, uncertainty):
+    """ActiveLearning.coreset_selection (ActiveLearning.py:798-850), same `self` attributes:
+    labeled_id, moks_queried, unc_lambda, uncertainty (the strategy name), cfg.VAL.UNC_LAMBDA,
+    opt.fixed_lambda, query_size.  `uncertainty` (the array) is modified in place like the
+    reference (:848).  Returns the list of picked indices in pick order."""
+    X = _as_cuda(embeddings, torch.float32)
+    if isinstance(embeddings, np.ndarray) and embeddings.dtype == np.float64:
+        if not np.array_equal(X.cpu().numpy().astype(np.float64), embeddings):
+            raise _lib.VatlqError("embeddings must hold fp32-representable values (ActiveLearning.py:270,286)")
+    unc = _as_cuda(uncertainty, torch.float64)
+    labeled = list(self.labeled_id.index)
+    first_pick = -1
+    if self.uncertainty == "None" or self.cfg.VAL.UNC_LAMBDA == 0:
+        rule = "dist"
+        if len(labeled) == 0:   # _query (:828-833): random first pick, drawn like the reference
+            first_pick = int(np.random.choice(np.arange(X.shape[0])))
+    elif self.opt.fixed_lambda:
+        rule = "fixed_lambda"
+    else:
+        rule = "w_unc"
+    picks, stats, _, unc_after = ops.coreset_select(
+        X, unc, labeled, int(self.query_size), float(self.moks_queried), float(self.unc_lambda), rule=rule,
+        first_pick=first_pick, batch=int(getattr(self, "coreset_batch", 8)), return_state=True)
+    self.coreset_stats = stats
+    if isinstance(uncertainty, np.ndarray):
+        uncertainty[:] = unc_after.cpu().numpy()
+    return [int(i) for i in picks.cpu().tolist()]
+
+
+# ----------------------------------------------------------------------------------------
+# the controller
+# ----------------------------------------------------------------------------------------
+
+_REFERENCE_ONLY_UNC = ("HP", "TPC", "MPE", "VL4Pose", "Entropy", "Margin")
+
+
+class ActiveLearning:
+    """Query-pass controller with the reference's public surface: `ActiveLearning(cfg, opt)`,
+    `eval_and_query()`, `outcome()` and the state they mutate (ActiveLearning.py:52-164,253-649,
+    166-205).  The estimator, the evaluation data loader and the auto-encoder are injected
+    (`model`, `eval_loader`, `AE`); `eval_loader` yields the reference's collate tuple
+    (idxs, inps, labels, label_masks, GTkpts, img_ids, ann_ids, bboxes_crop, bboxes_ann, isPrev, isNext)
+    (alphapose/datasets/posetrack21.py:207-) in pool order."""
+
+    def __init__(self, cfg, opt, model=None, eval_loader=None, eval_len=None, AE=None, oks_fn=None,
+                 eval_hook=None, retrain_hook=None):
+        self.round_cnt = 0
+        self.cfg, self.opt = cfg, opt
+        self.strategy = opt.strategy
+        self.uncertainty = opt.uncertainty
+        self.representativeness = opt.representativeness
+        self.filter = opt.filter
+        self.video_id = getattr(opt, "video_id", None)
+        self.get_prenext = getattr(opt, "get_prenext", ("THC" in self.uncertainty or self.uncertainty == "TPC"))
+        self.model, self.eval_loader, self.AE = model, eval_loader, AE
+        self.oks_fn, self.eval_hook, self.retrain_hook = oks_fn, eval_hook, retrain_hook
+        # dispatch keys: accept exactly the reference's names (:329-401,467-481,533-619)
+        u = self.uncertainty
+        known = u in ("None", "THC+WPU") or "THC" in u or "WPU" in u or u in _REFERENCE_ONLY_UNC
+        if not known:
+            raise ValueError("Uncertainty type is not supported")
+        if self.representativeness not in ("None", "Influence", "Random"):
+            raise ValueError("Representativeness type is not supported")
+        if self.filter not in ("None", "weighted", "K-Means", "Coreset", "Diversity", "Random"):
+            raise ValueError("Filter type is not supported")
+        self.eval_len = int(eval_len if eval_len is not None else len(eval_loader.dataset))
+        self.query_ratio = cfg.VAL.QUERY_RATIO
+        self.w_unc = cfg.VAL.W_UNC
+        self.unc_lambda = cfg.VAL.UNC_LAMBDA
+        self.query_sizes = [int(self.eval_len * x) for x in self.query_ratio]
+        self.query_size = self.query_sizes[0]
+        if getattr(opt, "onebyone", False):
+            self.query_size = 3
+        self.unlabeled_id = IndexCollection(list(range(self.eval_len)))
+        self.labeled_id = IndexCollection()
+        self.percentage, self.combine_weight = [], []
+        self.query_list_list, self.uncertainty_dict, self.influence_dict = {}, {}, {}
+        self.uncertainty_mean, self.moksQ_list = [], []
+        self.moks_queried = 0
+        self.is_early_stop = False
+        self.eval_joints = list(range(ops.J))
+        self.hm_size = cfg.DATA_PRESET.HEATMAP_SIZE
+        self.coreset_batch = int(getattr(opt, "coreset_batch", 8))
+        self.last_query = None
+
+    # -- dispatch guard: names this package does not accelerate stay on the reference ----
+    def _require_accelerated(self):
+        u = self.uncertainty
+        if u in _REFERENCE_ONLY_UNC:
+            raise NotImplementedError(
+                f"uncertainty '{u}' is not on the accelerated path: run the reference's "
+                "ActiveLearning.eval_and_query (active_learning/ActiveLearning.py:329-401) for it")
+        if self.representativeness != "None":
+            raise NotImplementedError("representativeness '%s': use the reference (ActiveLearning.py:467-483)"
+                                      % self.representativeness)
+        if self.filter not in ("None", "Coreset"):
+            raise NotImplementedError("filter '%s': use the reference (ActiveLearning.py:541-619)" % self.filter)
+
+    @torch.no_grad()
+    def eval_and_query(self):
+        """ActiveLearning.eval_and_query (:253-649): estimator forward stays the caller's model;
+        scoring, fusion and selection run on the device."""
+        self._require_accelerated()
+        dev = _dev()
+        n = self.eval_len
+        use_wpu = "WPU" in self.uncertainty
+        want_feat = self.filter not in ("None", "Random")   # (:283)
+        qp = QueryPass(n, dev, ae_weights=self.AE if use_wpu else None, uncertainty=self.uncertainty)
+        X = torch.zeros((n, 2048), dtype=torch.float32, device=dev) if want_feat else None
+        m = self.model
+        if hasattr(m, "eval"):
+            m.eval()
+        strict = bool(getattr(self.opt, "strict_prenext", False)) and "THC" in self.uncertainty
+        thc_strict = torch.zeros(n, dtype=torch.float32, device=dev) if strict else None
+        pos = 0
+        for batch in self.eval_loader:
+            idxs, inps = batch[0], batch[1]
+            bboxes_crop, isPrev, isNext = batch[7], batch[9], batch[10]
+            idx_t = torch.as_tensor(np.asarray(idxs)).long()
+            b = idx_t.numel()
+            if not torch.equal(idx_t, torch.arange(pos, pos + b)):
+                raise _lib.VatlqError("eval_loader must walk the id-sorted pool in order (shuffle=False)")
+            cur = inps[:, 0].to(dev)
+            H = m(cur)[:, self.eval_joints].float().contiguous()          # (:277-281)
+            if want_feat:
+                emb = m.module.get_embedding(cur) if hasattr(m, "module") else m.get_embedding(cur)
+                X[pos:pos + b] = emb.float()                              # (:283-286)
+            boxes = torch.as_tensor(np.asarray(bboxes_crop), dtype=torch.float32).reshape(b, 4).to(dev)
+            ip = torch.as_tensor(np.asarray(isPrev)).to(torch.uint8)
+            inx = torch.as_tensor(np.asarray(isNext)).to(torch.uint8)
+            qp.score_chunk(pos, H, boxes, ip, inx)
+            if strict:   # the reference's own three forwards (:293-297)
+                Hp = m(inps[:, 1].to(dev))[:, self.eval_joints].float().contiguous()
+                Hn = m(inps[:, 2].to(dev))[:, self.eval_joints].float().contiguous()
+                thc_strict[pos:pos + b] = ops.thc3(H, Hp, Hn, ip, inx)
+            if self.eval_hook is not None:
+                self.eval_hook(self, batch, qp.kpts[pos:pos + b])
+            pos += b
+        if pos != n:
+            raise _lib.VatlqError(f"eval_loader produced {pos} items, expected {n}")
+        if strict:
+            qp.thc.copy_(thc_strict)
+        return self._query(qp, X)
+
+    def _query(self, qp: QueryPass, X):
+        """Everything after the per-person loop: :465-649."""
+        dev = qp.dev
+        n = self.eval_len
+        unl_idx = self.unlabeled_id.index
+        unl = torch.zeros(n, dtype=torch.uint8, device=dev)
+        if unl_idx:
+            unl[torch.as_tensor(unl_idx, device=dev)] = 1
+        thc_h = qp.thc.cpu().numpy() if qp.use_thc else None
+        wpu_h = qp.wpu.cpu().numpy() if qp.use_wpu else None
+        if self.uncertainty == "THC+WPU":
+            total_unc = float(thc_h.astype(np.float64).sum())
+            UNC = {i: [float(thc_h[i]), float(wpu_h[i])] for i in range(n)}
+        elif qp.use_thc or qp.use_wpu:
+            v = thc_h if qp.use_thc else wpu_h
+            total_unc = float(v.astype(np.float64).sum())
+            UNC = {i: float(v[i]) for i in range(n)}
+        else:
+            total_unc, UNC = 0.0, {i: 0 for i in range(n)}
+        self.uncertainty_mean.append(total_unc / n)                                   # (:466)
+        self.percentage.append(len(self.labeled_id) / n * 100)
+        score = qp.fuse(unl, getattr(self.opt, "THCvsWPU", "const"), labeled_ratio=len(self.labeled_id) / n)
+        if len(unl_idx) > 0:
+            self.combine_weight.append(qp.combine_weight)                             # (:486-488)
+        if self.uncertainty != "None" and len(unl_idx) not in (0, 1):
+            self.uncertainty_dict["Round" + str(self.round_cnt)] = UNC                # (:510,514)
+        if len(unl_idx) in (0, 1) or self.filter == "None":
+            # top query_size by score, ties in unlabelled-id order (sorted() is stable) (:527-540)
+            s = score.cpu().numpy()[unl_idx] if unl_idx else np.zeros(0)
+            order = sorted(range(len(unl_idx)), key=lambda t: s[t], reverse=True)
+            query_list = sorted(int(unl_idx[t]) for t in order[:self.query_size])
+        else:                                                                          # Coreset (:609-614)
+            holder = SimpleNamespace(labeled_id=self.labeled_id, moks_queried=self.moks_queried,
+                                     unc_lambda=self.unc_lambda, uncertainty=self.uncertainty, cfg=self.cfg,
+                                     opt=self.opt, query_size=self.query_size, coreset_batch=self.coreset_batch)
+            query_list = coreset_selection(holder, X, score)
+            self.coreset_stats = holder.coreset_stats
+        self.last_query = SimpleNamespace(thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts,
+                                          score=score, query_list=list(query_list))
+        if len(unl_idx) != 0:                                                          # (:629-637)
+            if self.oks_fn is not None:
+                oks = np.asarray(self.oks_fn(query_list, qp.kpts), dtype=np.float64)
+                self.moks_queried = float(np.mean(oks)) if oks.size else 0
+                self.moksQ_list.append(self.moks_queried)
+            self.labeled_id.update(query_list)
+            self.unlabeled_id.difference_update(query_list)
+            self.query_list_list["Round" + str(self.round_cnt)] = list(map(int, query_list))
+        return None
+
+    def outcome(self):
+        """Control flow of ActiveLearning.outcome (:166-205).  Retraining itself (:651-686) is the
+        caller's `retrain_hook(self)`.  Returns None while rounds remain; when finished, a dict
+        with the query-side members of the reference's 20-tuple (:203)."""
+        if self.is_early_stop or getattr(self.opt, "onebyone", False):
+            finish = True
+        else:
+            if self.retrain_hook is not None:
+                self.retrain_hook(self)
+            self.round_cnt += 1
+            if len(self.unlabeled_id) == 0:
+                self.eval_and_query()   # final evaluation round (:191-193)
+                finish = True
+            else:
+                if self.round_cnt >= len(self.query_ratio):
+                    self.query_size = len(self.unlabeled_id)                          # (:197-198)
+                else:
+                    self.query_size = self.query_sizes[self.round_cnt] - len(self.labeled_id)   # (:199-200)
+                finish = False
+        if not finish:
+            return None
+        return dict(percentage=self.percentage, query_list_list=self.query_list_list,
+                    uncertainty_dict=self.uncertainty_dict, uncertainty_mean=self.uncertainty_mean,
+                    influence_dict=self.influence_dict, combine_weight=self.combine_weight,
+                    moksQ_list=self.moksQ_list)

@@ -1,0 +1,85 @@
+// Shared helpers for libvatlq (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/vatlq.h"
+
+namespace vatlq {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+#define VQ_REQUIRE(cond, msg)                                                       \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      snprintf(::vatlq::g_err, sizeof(::vatlq::g_err), "%s: %s", __func__, msg);    \
+      return VATLQ_EINVAL;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define VQ_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      snprintf(::vatlq::g_err, sizeof(::vatlq::g_err), "%s:%d %s -> %s", __FILE__, \
+               __LINE__, #expr, cudaGetErrorString(_e));                           \
+      return (int)_e;                                                              \
+    }                                                                              \
+  } while (0)
+
+// count + check a kernel launch
+#define VQ_LAUNCHED()                     \
+  do {                                    \
+    ::vatlq::g_launches.fetch_add(1);     \
+    VQ_CUDA(cudaGetLastError());          \
+  } while (0)
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int fill_f64(double* p, long long n, double v, cudaStream_t stream);
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// fixed-order butterfly: every lane ends with the same bits
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace vatlq

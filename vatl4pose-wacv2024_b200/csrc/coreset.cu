@@ -1,0 +1,1041 @@
+// k-center greedy core-set selection (ActiveLearning.coreset_selection,
+// active_learning/ActiveLearning.py:798-850) with fp64 distance arithmetic on fp32 features.
+//
+// One canonical distance d(i,c) is used everywhere (same summation order in every kernel):
+//   dot(i,c): lane l of a warp accumulates the float4 chunks q = l, l+32, ... of the rows with
+//             an fp64 FMA chain (products of fp32 values are exact in fp64), then a fixed xor
+//             butterfly adds the 32 partials;
+//   d(i,c) = sqrt(max(0, (-2*dot + xx_i) + xx_c))   (sklearn _euclidean_distances order).
+//
+// Exact batching: scores only ever decrease, so the next greedy picks
+// can be decided in advance on the candidate set {score >= theta}: as long as the best
+// surviving candidate still scores >= theta it beats every non-candidate (all < theta), ties
+// resolving to the lowest index exactly like np.argmax.  One pass over X then applies up to
+// kB picks at once, reading every row of X from HBM once instead of kB times.
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace vatlq {
+
+constexpr int kB = 8;        // picks applied per pass over X
+constexpr int kR = 4;        // rows per warp step (register tile kR x kB)
+constexpr int kPassThreads = 256;
+constexpr int kCapL = 1024;  // candidate records per rank
+constexpr int kCap = 1024;   // candidates the planner handles (one per thread)
+constexpr int kNB = 1024;    // score-histogram bins
+constexpr int kTarget = 256; // wanted candidates per round (all ranks together)
+constexpr int kMaxRanks = 16;
+constexpr int kMaxSmem = 200 * 1024;
+
+struct RankBlock {  // the all-gather unit: one per rank per round
+  long long count;  // rows with score >= theta (records beyond kCapL are dropped -> overflow)
+  double theta;     // every owned row with score >= theta is listed below
+  double smax;      // exact maximum score of the owned rows ...
+  long long smax_idx;  // ... and its lowest index
+  long long inwin;  // owned rows inside the histogram window
+  long long pad[3];
+  long long idx[kCapL];
+  double m[kCapL];
+  double unc[kCapL];
+  double score[kCapL];
+};
+
+struct Ctl {
+  long long n_picked, k;
+  long long picks[kB];
+  int nb;           // picks the next pass applies
+  int first_round;  // labelled set empty: score = unc, exactly one pick (ActiveLearning.py:816-818)
+  int rule, world;
+  int maxb, pad1;   // picks per pass allowed (1 = GEMV form: plain argmax every round)
+  double wd, wu;    // score = wd*min_d + wu*unc
+  double U, W;      // histogram window [U-W, U]; W <= 0: no window yet
+  unsigned int filter_ticket, pad0;
+  long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
+};
+
+struct Best {
+  double s;
+  long long i;
+};
+__device__ __forceinline__ bool better(double s, long long i, double s2, long long i2) {
+  return (s > s2) || (s == s2 && i < i2);  // np.argmax: first index of the maximum
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double s2 = __shfl_xor_sync(0xffffffffu, b.s, o);
+    const long long i2 = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (better(s2, i2, b.s, b.i)) {
+      b.s = s2;
+      b.i = i2;
+    }
+  }
+  return b;
+}
+
+__device__ __forceinline__ double score_of(int rule, double wd, double wu, double m, double u) {
+  if (rule == 0) return __dadd_rn(__dmul_rn(wd, m), __dmul_rn(wu, u));  // :819
+  if (rule == 1) return __dadd_rn(m, __dmul_rn(wu, u));                  // :826 (wu = lambda)
+  return m;                                                              // :832
+}
+
+__device__ __forceinline__ double dist_from_dot(double dot, double xxi, double xxc) {
+  double t = __dmul_rn(-2.0, dot);
+  t = __dadd_rn(t, xxi);
+  t = __dadd_rn(t, xxc);
+  return sqrt(fmax(t, 0.0));
+}
+
+// ---- candidate rows in shared memory: fp64, laid out so that lane l's chunk of iteration
+// `it` is two conflict-free double2 loads: s_c[((j*nit + it)*2 + half)*32 + l]
+__device__ __forceinline__ void stage_center(const float* __restrict__ X, int d4, int nit, long long row, int j,
+                                             double2* s_c) {
+  const float4* src = reinterpret_cast<const float4*>(X) + (size_t)row * d4;
+  for (int q = threadIdx.x; q < nit * 32; q += blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < d4) v = __ldg(src + q);
+    const int base = ((j * nit + (q >> 5)) * 2) * 32 + (q & 31);
+    s_c[base] = make_double2((double)v.x, (double)v.y);
+    s_c[base + 32] = make_double2((double)v.z, (double)v.w);
+  }
+}
+
+// canonical dot products of kR rows against NBK staged centers; every lane ends with all sums
+template <int NBK>
+__device__ __forceinline__ void dot_tile(const float4* const (&rowp)[kR], int d4, int nit, const double2* __restrict__ s_c,
+                                         int lane, double (&acc)[kR][NBK]) {
+#pragma unroll
+  for (int r = 0; r < kR; ++r)
+#pragma unroll
+    for (int j = 0; j < NBK; ++j) acc[r][j] = 0.0;
+#pragma unroll 2
+  for (int it = 0; it < nit; ++it) {
+    const int q = it * 32 + lane;
+    float4 xv[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rowp[r] != nullptr && q < d4) xv[r] = ldg_stream(rowp[r] + q);
+    }
+#pragma unroll
+    for (int j = 0; j < NBK; ++j) {
+      const double2 c01 = s_c[((j * nit + it) * 2) * 32 + lane];
+      const double2 c23 = s_c[((j * nit + it) * 2 + 1) * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        double a = acc[r][j];
+        a = fma((double)xv[r].x, c01.x, a);
+        a = fma((double)xv[r].y, c01.y, a);
+        a = fma((double)xv[r].z, c23.x, a);
+        a = fma((double)xv[r].w, c23.y, a);
+        acc[r][j] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kR; ++r)
+#pragma unroll
+    for (int j = 0; j < NBK; ++j) acc[r][j] = warp_sum(acc[r][j]);
+}
+
+// ---------------------------------------------------------------- squared row norms
+__global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ X, long long n, int d4,
+                                                        double* __restrict__ xx) {
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = w; i < n; i += nw) {
+    const float4* p = reinterpret_cast<const float4*>(X) + (size_t)i * d4;
+    double a = 0.0;
+    for (int q = lane; q < d4; q += 32) {
+      const float4 v = ldg_stream(p + q);
+      a = fma((double)v.x, (double)v.x, a);
+      a = fma((double)v.y, (double)v.y, a);
+      a = fma((double)v.z, (double)v.z, a);
+      a = fma((double)v.w, (double)v.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) xx[i] = a;
+  }
+}
+
+// ---------------------------------------------------------------- the pass over X
+struct PassArgs {
+  const float* X;
+  long long n;
+  int d4, nit;
+  long long lo, hi;          // owned rows
+  const double* xx;
+  double* m;
+  double* unc;               // null: distance-only pass (labelled-set initialisation)
+  double* score;
+  const long long* centers;  // device list of centers to apply
+  const int* n_centers;      // device count (<= kB), or null -> n_centers_imm
+  int n_centers_imm;
+  Ctl* ctl;                  // null for initialisation passes
+  unsigned int* hist;        // null: no histogram
+};
+
+template <int NBK>
+__device__ __forceinline__ void pass_body(const PassArgs& a, int nb, double2* s_c, double* s_xxc, long long* s_pick,
+                                          unsigned int* s_hist) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int j = 0; j < NBK; ++j) {
+    const long long p = a.centers[min(j, nb - 1)];  // pad with the last pick: min() is idempotent
+    stage_center(a.X, a.d4, a.nit, p, j, s_c);
+    if (threadIdx.x == 0) {
+      s_xxc[j] = a.xx[p];
+      s_pick[j] = p;
+    }
+  }
+  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+  double h_lo = 0.0, h_inv = 0.0;
+  int rule = 0;
+  double wd = 0.0, wu = 0.0;
+  if (a.ctl) {
+    rule = a.ctl->rule;
+    wd = a.ctl->wd;
+    wu = a.ctl->wu;
+    if (do_hist) {
+      h_lo = a.ctl->U - a.ctl->W;
+      h_inv = (double)kNB / a.ctl->W;
+      for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
+    }
+  }
+  __syncthreads();
+  const float4* X4 = reinterpret_cast<const float4*>(a.X);
+  const long long stride = (long long)gridDim.x * nwarp * kR;
+  for (long long g = a.lo + ((long long)blockIdx.x * nwarp + warp) * kR; g < a.hi; g += stride) {
+    const float4* rowp[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) rowp[r] = (g + r < a.hi) ? X4 + (size_t)(g + r) * a.d4 : nullptr;
+    double acc[kR][NBK];
+    dot_tile<NBK>(rowp, a.d4, a.nit, s_c, lane, acc);
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      if (lane == r && g + r < a.hi) {
+        const long long i = g + r;
+        const double xxi = a.xx[i];
+        double dmin = a.m[i];
+        bool picked = false;
+#pragma unroll
+        for (int j = 0; j < NBK; ++j) {
+          dmin = fmin(dmin, dist_from_dot(acc[r][j], xxi, s_xxc[j]));
+          picked = picked || (s_pick[j] == i);
+        }
+        a.m[i] = dmin;
+        if (a.unc) {
+          double u = a.unc[i];
+          if (picked) {
+            u = 0.0;  // uncertainty[ind] = 0  (:848)
+            a.unc[i] = 0.0;
+          }
+          const double sc = score_of(rule, wd, wu, dmin, u);
+          a.score[i] = sc;
+          if (do_hist) {
+            const double fb = (sc - h_lo) * h_inv;
+            if (fb >= 0.0) {
+              int b = (int)fmin(fb, (double)(kNB - 1));
+              atomicAdd(&s_hist[b], 1u);
+              atomicAdd(&s_hist[kNB], 1u);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (do_hist) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x)
+      if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
+  }
+}
+
+template <int MAXB>
+__global__ void __launch_bounds__(kPassThreads, (MAXB == 1) ? 2 : 1) pass_kernel(PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  if (nb <= 0) return;
+  // NBK is the power of two >= nb; the staging area is sized for MAXB by the host
+  const int nbk = nb <= 1 ? 1 : (nb <= 2 ? 2 : (nb <= 4 ? 4 : 8));
+  double2* s_c = reinterpret_cast<double2*>(smem_raw);
+  double* s_xxc = reinterpret_cast<double*>(s_c + (size_t)MAXB * a.nit * 64);
+  long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
+  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  if (MAXB == 1) {
+    pass_body<1>(a, 1, s_c, s_xxc, s_pick, s_hist);
+    return;
+  }
+  switch (nbk) {
+    case 1: pass_body<1>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
+    case 2: pass_body<2>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
+    case 4: pass_body<(MAXB >= 4 ? 4 : 1)>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
+    default: pass_body<(MAXB >= 8 ? 8 : 1)>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
+  }
+}
+
+static size_t pass_smem_bytes(int nit, int nbk) {
+  return (size_t)nbk * nit * 64 * sizeof(double2) + kB * sizeof(double) + kB * sizeof(long long) +
+         (kNB + 1) * sizeof(unsigned int);
+}
+
+// ---------------------------------------------------------------- initial scores
+__global__ void __launch_bounds__(256) score_init_kernel(long long lo, long long hi, const double* __restrict__ m,
+                                                         const double* __restrict__ unc, double* __restrict__ score,
+                                                         const Ctl* ctl) {
+  const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  score[i] = ctl->first_round ? unc[i] : score_of(ctl->rule, ctl->wd, ctl->wu, m[i], unc[i]);
+}
+
+// ---------------------------------------------------------------- candidate filter
+__global__ void __launch_bounds__(256) filter_kernel(long long lo, long long hi, const double* __restrict__ m,
+                                                     const double* __restrict__ unc, const double* __restrict__ score,
+                                                     unsigned int* hist, Best* partial, RankBlock* out, Ctl* ctl) {
+  if (ctl->n_picked >= ctl->k) return;
+  __shared__ unsigned int s_cum[kNB];
+  __shared__ double s_theta;
+  __shared__ Best s_best[8];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x;
+  // theta from the score histogram the last pass left behind (identical in every CTA)
+  const double U = ctl->U, W = ctl->W;
+  const int target = max(1, kTarget / max(1, ctl->world));
+  const bool windowed = W > 0.0 && ctl->maxb > 1;
+  if (windowed) {
+    // suffix sums: 256 threads x 4 bins, then a serial pass over 256 chunk totals by thread 0
+    unsigned int h[4], tot = 0;
+#pragma unroll
+    for (int c = 3; c >= 0; --c) {
+      tot += hist[tid * 4 + c];
+      h[c] = tot;
+    }
+    s_cum[tid * 4 + 0] = h[0];
+    s_cum[tid * 4 + 1] = h[1];
+    s_cum[tid * 4 + 2] = h[2];
+    s_cum[tid * 4 + 3] = h[3];
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int run = 0;
+      int bstar = -1;    // highest bin whose suffix count reaches the target
+      int bfit = kNB;    // lowest bin whose suffix count still fits the record capacity
+      for (int c = 255; c >= 0; --c) {
+        for (int e = 3; e >= 0; --e) {
+          const unsigned int cum = run + s_cum[c * 4 + e];
+          const int b = c * 4 + e;
+          if (cum <= (unsigned)kCapL) bfit = b;
+          if (bstar < 0 && cum >= (unsigned)target) bstar = b;
+        }
+        run += s_cum[c * 4];
+      }
+      if (bstar < 0) bstar = 0;
+      double th;
+      if (bfit == kNB) th = INFINITY;  // even the top bin overflows: exact-argmax fallback
+      else {
+        const int b = max(bstar, bfit);
+        th = (b == 0) ? (U - W) : (U - W) + (double)b * (W / (double)kNB);
+      }
+      s_theta = th;
+    }
+  } else if (tid == 0) {
+    s_theta = INFINITY;
+  }
+  __syncthreads();
+  const double theta = s_theta;
+  Best best{-INFINITY, 0x7fffffffffffffffLL};
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + tid; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    const double s = score[i];
+    if (better(s, i, best.s, best.i)) {
+      best.s = s;
+      best.i = i;
+    }
+    if (s >= theta) {
+      const unsigned long long pos = atomicAdd((unsigned long long*)&out->count, 1ULL);
+      if (pos < (unsigned long long)kCapL) {
+        out->idx[pos] = i;
+        out->m[pos] = m[i];
+        out->unc[pos] = unc[i];
+        out->score[pos] = s;
+      }
+    }
+  }
+  best = warp_best(best);
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < 8; ++k)
+      if (better(s_best[k].s, s_best[k].i, best.s, best.i)) best = s_best[k];
+    partial[blockIdx.x] = best;
+    __threadfence();
+    s_last = (atomicAdd(&ctl->filter_ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    Best b{-INFINITY, 0x7fffffffffffffffLL};
+    for (int k = tid; k < (int)gridDim.x; k += blockDim.x) {
+      Best p;
+      p.s = ((volatile Best*)partial)[k].s;
+      p.i = ((volatile Best*)partial)[k].i;
+      if (better(p.s, p.i, b.s, b.i)) b = p;
+    }
+    b = warp_best(b);
+    if ((tid & 31) == 0) s_best[tid >> 5] = b;
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < 8; ++k)
+        if (better(s_best[k].s, s_best[k].i, b.s, b.i)) b = s_best[k];
+      out->smax = b.s;
+      out->smax_idx = b.i;
+      out->theta = theta;
+      out->inwin = windowed ? (long long)hist[kNB] : 0;
+      ctl->filter_ticket = 0;
+    }
+    // every CTA has consumed the histogram (it is read before the ticket): clear it
+    for (int k = tid; k < kNB + 1; k += blockDim.x) hist[k] = 0u;
+  }
+}
+
+// ---------------------------------------------------------------- candidate bookkeeping
+struct CandView {
+  int total;        // candidates over all ranks (records actually stored)
+  int fallback;     // 0 plan on candidates, 1 nothing listed, 2 overflow
+  double theta;     // max over ranks
+  int start[kMaxRanks + 1];
+};
+__device__ __forceinline__ CandView view_of(const RankBlock* blocks, int world) {
+  CandView v;
+  v.total = 0;
+  v.fallback = 0;
+  v.theta = -INFINITY;
+  bool overflow = false;
+  for (int r = 0; r < world; ++r) {
+    v.start[r] = v.total;
+    const long long c = blocks[r].count;
+    if (c > kCapL) overflow = true;
+    v.total += (int)min(c, (long long)kCapL);
+    v.theta = fmax(v.theta, blocks[r].theta);
+  }
+  v.start[world] = v.total;
+  if (overflow || v.total > kCap || isinf(v.theta)) v.fallback = 2;
+  else if (v.total == 0) v.fallback = 1;
+  return v;
+}
+__device__ __forceinline__ void locate(const CandView& v, int world, int pos, int& r, int& s) {
+  r = 0;
+  while (r + 1 < world && pos >= v.start[r + 1]) ++r;
+  s = pos - v.start[r];
+}
+
+// ---------------------------------------------------------------- candidate x candidate distances
+__global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X, int d4, int nit,
+                                                    const double* __restrict__ xx, const RankBlock* blocks,
+                                                    const Ctl* ctl, double* __restrict__ Dcc) {
+  if (ctl->n_picked >= ctl->k) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_xxc[kB];
+  const int world = ctl->world;
+  const CandView v = view_of(blocks, world);
+  if (v.fallback) return;
+  const int col0 = blockIdx.x * kB;
+  if (col0 >= v.total) return;
+  double2* s_c = reinterpret_cast<double2*>(smem_raw);
+  for (int j = 0; j < kB; ++j) {
+    int r, s;
+    locate(v, world, min(col0 + j, v.total - 1), r, s);
+    const long long p = blocks[r].idx[s];
+    stage_center(X, d4, nit, p, j, s_c);
+    if (threadIdx.x == 0) s_xxc[j] = xx[p];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  for (int g = (blockIdx.y * nwarp + warp) * kR; g < v.total; g += gridDim.y * nwarp * kR) {
+    const float4* rowp[kR];
+    long long ridx[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      rowp[r] = nullptr;
+      ridx[r] = -1;
+      if (g + r < v.total) {
+        int rr, ss;
+        locate(v, world, g + r, rr, ss);
+        ridx[r] = blocks[rr].idx[ss];
+        rowp[r] = X4 + (size_t)ridx[r] * d4;
+      }
+    }
+    double acc[kR][kB];
+    dot_tile<kB>(rowp, d4, nit, s_c, lane, acc);
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      if (lane == r && ridx[r] >= 0) {
+        const double xxi = xx[ridx[r]];
+#pragma unroll
+        for (int j = 0; j < kB; ++j)
+          if (col0 + j < v.total) Dcc[(size_t)(g + r) * kCap + col0 + j] = dist_from_dot(acc[r][j], xxi, s_xxc[j]);
+      }
+    }
+  }
+}
+
+// exact global argmax from the per-rank headers: always the correct next greedy pick
+__device__ void fallback_pick(const RankBlock* blocks, int world, int kind, RankBlock* send,
+                              long long* __restrict__ out_idx, Ctl* ctl) {
+  Best b{-INFINITY, 0x7fffffffffffffffLL};
+  for (int r = 0; r < world; ++r) {
+    if (better(blocks[r].smax, blocks[r].smax_idx, b.s, b.i)) {
+      b.s = blocks[r].smax;
+      b.i = blocks[r].smax_idx;
+    }
+  }
+  ctl->picks[0] = b.i;
+  ctl->nb = 1;
+  out_idx[ctl->n_picked] = b.i;
+  ctl->n_picked += 1;
+  ctl->stat_rounds += 1;
+  if (ctl->first_round) {
+    // the score changes meaning after the first pick (unc -> distance mix): no bound yet
+    ctl->first_round = 0;
+    ctl->U = 0.0;
+    ctl->W = -1.0;  // next round: plain argmax again, then U = smax
+  } else if (ctl->maxb > 1) {
+    double W = ctl->W;
+    ctl->U = b.s;  // scores only decrease
+    if (kind == 2) {
+      ctl->stat_fallback_overflow += 1;
+      W = (W > 0.0) ? W / 16.0 : b.s / 64.0;
+    } else {
+      ctl->stat_fallback_empty += 1;
+      W = (W > 0.0) ? fmin(b.s, W * 4.0) : b.s / 64.0;
+    }
+    if (!(W > 0.0)) W = b.s;
+    ctl->W = W;
+  }
+  send->count = 0;
+}
+
+// ---------------------------------------------------------------- the planner: exact greedy on candidates
+__global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, RankBlock* send, const double* __restrict__ Dcc,
+                                                    long long* __restrict__ out_idx, Ctl* ctl) {
+  __shared__ Best s_b[32];
+  __shared__ int s_pos[32];
+  __shared__ Best s_win;
+  __shared__ int s_winpos;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ctl->n_picked >= ctl->k) {
+    if (tid == 0) ctl->nb = 0;
+    return;
+  }
+  const int world = ctl->world;
+  const CandView v = view_of(blocks, world);
+  const int rule = ctl->rule;
+  const double wd = ctl->wd, wu = ctl->wu;
+  const long long remaining = ctl->k - ctl->n_picked;
+  if (v.fallback) {
+    if (tid == 0) fallback_pick(blocks, world, v.fallback, send, out_idx, ctl);
+    return;
+  }
+  // one candidate per thread
+  long long idx = 0x7fffffffffffffffLL;
+  double m = 0.0, u = 0.0, sc = -INFINITY;
+  if (tid < v.total) {
+    int r, s;
+    locate(v, world, tid, r, s);
+    idx = blocks[r].idx[s];
+    m = blocks[r].m[s];
+    u = blocks[r].unc[s];
+    sc = blocks[r].score[s];
+  }
+  const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kB, ctl->maxb)), remaining);
+  int nb = 0;
+  for (int b = 0; b < maxpicks; ++b) {
+    Best me{sc, idx};
+    int pos = tid;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double s2 = __shfl_xor_sync(0xffffffffu, me.s, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, me.i, o);
+      const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+      if (better(s2, i2, me.s, me.i)) {
+        me.s = s2;
+        me.i = i2;
+        pos = p2;
+      }
+    }
+    if (lane == 0) {
+      s_b[warp] = me;
+      s_pos[warp] = pos;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      Best w = s_b[lane];
+      int p = s_pos[lane];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const double s2 = __shfl_xor_sync(0xffffffffu, w.s, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, w.i, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
+        if (better(s2, i2, w.s, w.i)) {
+          w.s = s2;
+          w.i = i2;
+          p = p2;
+        }
+      }
+      if (lane == 0) {
+        s_win = w;
+        s_winpos = p;
+      }
+    }
+    __syncthreads();
+    const Best win = s_win;
+    const int wpos = s_winpos;
+    __syncthreads();
+    if (!(win.s >= v.theta)) {  // a non-candidate (score < theta) could be ahead now
+      if (b == 0) {             // (only possible when the rank that set theta listed nothing)
+        if (tid == 0) fallback_pick(blocks, world, 1, send, out_idx, ctl);
+        return;
+      }
+      break;
+    }
+    if (tid == 0) {
+      ctl->picks[nb] = win.i;
+      out_idx[ctl->n_picked + nb] = win.i;
+    }
+    nb += 1;
+    if (tid < v.total) {
+      m = fmin(m, Dcc[(size_t)tid * kCap + wpos]);
+      if (tid == wpos) u = 0.0;
+      sc = score_of(rule, wd, wu, m, u);
+    }
+  }
+  // best surviving candidate score -> upper bound of every score after the pass
+  Best me{sc, idx};
+  me = warp_best(me);
+  if (lane == 0) s_b[warp] = me;
+  __syncthreads();
+  if (tid == 0) {
+    Best b = s_b[0];
+    for (int k = 1; k < 32; ++k)
+      if (better(s_b[k].s, s_b[k].i, b.s, b.i)) b = s_b[k];
+    long long inwin = 0;
+    for (int r = 0; r < world; ++r) inwin += blocks[r].inwin;
+    const double U = ctl->U;
+    double W = ctl->W;
+    const double frac = (U - v.theta) / W;
+    if (inwin < kTarget) W = fmin(U, W * 4.0);
+    else if (frac < 1.0 / 16.0) W = W * 0.5;
+    else if (frac > 0.5) W = fmin(U, W * 2.0);
+    ctl->U = fmax(b.s, v.theta);
+    ctl->W = W;
+    ctl->nb = nb;          // nb >= 1: the first winner is the global argmax (score >= theta)
+    ctl->n_picked += nb;
+    ctl->stat_rounds += 1;
+    ctl->stat_cand_sum += v.total;
+    ctl->first_round = 0;
+    send->count = 0;
+  }
+}
+
+// distances of every row to a list of centers, for the parity tests
+__global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__ X, long long n, int d4, int nit,
+                                                       const long long* __restrict__ centers, long long mcols,
+                                                       double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_xxc[kB];
+  double2* s_c = reinterpret_cast<double2*>(smem_raw);
+  const long long col0 = (long long)blockIdx.x * kB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  for (int j = 0; j < kB; ++j) stage_center(X, d4, nit, centers[min(col0 + j, mcols - 1)], j, s_c);
+  __syncthreads();
+  // squared norms with the canonical dot: center j against itself via the staged copy
+  if (warp == 0) {
+    for (int j = 0; j < kB; ++j) {
+      double a = 0.0;
+      for (int it = 0; it < nit; ++it) {
+        const double2 c01 = s_c[((j * nit + it) * 2) * 32 + lane], c23 = s_c[((j * nit + it) * 2 + 1) * 32 + lane];
+        a = fma(c01.x, c01.x, a);
+        a = fma(c01.y, c01.y, a);
+        a = fma(c23.x, c23.x, a);
+        a = fma(c23.y, c23.y, a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) s_xxc[j] = a;
+    }
+  }
+  __syncthreads();
+  for (long long g = ((long long)blockIdx.y * nwarp + warp) * kR; g < n; g += (long long)gridDim.y * nwarp * kR) {
+    const float4* rowp[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) rowp[r] = (g + r < n) ? X4 + (size_t)(g + r) * d4 : nullptr;
+    double acc[kR][kB];
+    dot_tile<kB>(rowp, d4, nit, s_c, lane, acc);
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      if (g + r < n) {
+        // xx_i with the same canonical order
+        double a = 0.0;
+        for (int q = lane; q < d4; q += 32) {
+          const float4 x = __ldg(rowp[r] + q);
+          a = fma((double)x.x, (double)x.x, a);
+          a = fma((double)x.y, (double)x.y, a);
+          a = fma((double)x.z, (double)x.z, a);
+          a = fma((double)x.w, (double)x.w, a);
+        }
+        a = warp_sum(a);
+        if (lane == r) {
+#pragma unroll
+          for (int j = 0; j < kB; ++j)
+            if (col0 + j < mcols) out[(size_t)(g + r) * mcols + col0 + j] = dist_from_dot(acc[r][j], a, s_xxc[j]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- NCCL through dlopen
+struct Id128 {  // ncclUniqueId is a 128-byte struct passed by value
+  char b[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    snprintf(g_err, sizeof(g_err), "NCCL not found: %s", dlerror());
+    return VATLQ_ECOMM;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+    snprintf(g_err, sizeof(g_err), "NCCL symbols missing");
+    return VATLQ_ECOMM;
+  }
+  g_nccl.lib = h;
+  return 0;
+}
+struct Comm {
+  void* nccl;
+  int rank, world;
+};
+
+// ---------------------------------------------------------------- workspace layout
+struct WsLayout {
+  size_t xx, score, hist, partial, send, recv, dcc, ctl, picks_init, total;
+};
+static WsLayout ws_layout(long long n, int world) {
+  WsLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  L.ctl = take(sizeof(Ctl));
+  L.xx = take((size_t)n * 8);
+  L.score = take((size_t)n * 8);
+  L.hist = take((kNB + 1) * 4);
+  L.partial = take(4096 * sizeof(Best));
+  L.send = take(sizeof(RankBlock));
+  L.recv = take(sizeof(RankBlock) * (size_t)kMaxRanks);
+  L.dcc = take((size_t)kCap * kCap * 8);
+  L.picks_init = take(kB * 8);
+  L.total = o;
+  return L;
+}
+
+}  // namespace vatlq
+
+using namespace vatlq;
+
+extern "C" size_t vatlq_coreset_workspace_bytes(int64_t n, int d, int batch) {
+  (void)d;
+  (void)batch;
+  if (n < 0) return 0;
+  return ws_layout(n, kMaxRanks).total;
+}
+
+static int check_x(const float* X, int64_t n, int d, int64_t lo, int64_t hi) {
+  VQ_REQUIRE(X != nullptr && ((uintptr_t)X & 15) == 0, "X must be a 16-byte aligned device pointer");
+  VQ_REQUIRE(n > 0 && d > 0 && (d & 3) == 0, "d must be a positive multiple of 4");
+  VQ_REQUIRE(0 <= lo && lo <= hi && hi <= n, "bad row range");
+  const int nit = (d / 4 + 31) / 32;
+  VQ_REQUIRE(pass_smem_bytes(nit, 1) <= (size_t)kMaxSmem, "d too large");
+  return 0;
+}
+static int max_nbk(int nit, int batch) {
+  // two builds of the pass: GEMV form (1 center) and the batched form (staging for kB centers)
+  if (batch <= 1 || pass_smem_bytes(nit, kB) > (size_t)kMaxSmem) return 1;
+  int nbk = 1;
+  while (nbk * 2 <= kB && nbk * 2 <= batch) nbk *= 2;
+  return nbk;
+}
+
+static int launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream_t stream) {
+  const int grid = sm_count() * 8;
+  row_norms_kernel<<<grid, 256, 0, stream>>>(X, n, d / 4, xx);
+  VQ_LAUNCHED();
+  return 0;
+}
+
+static int launch_pass(PassArgs& a, int nbk_max, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxSmem / 2)));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    configured = true;
+  }
+  if (nbk_max == 1) {
+    // GEMV form: a small staging area, two CTAs per SM for more loads in flight
+    const size_t smem = pass_smem_bytes(a.nit, 1);
+    pass_kernel<1><<<sm_count() * (smem <= (size_t)kMaxSmem / 2 ? 2 : 1), kPassThreads, smem, stream>>>(a);
+  } else {
+    const size_t smem = pass_smem_bytes(a.nit, 8);
+    pass_kernel<8><<<sm_count(), kPassThreads, smem, stream>>>(a);
+  }
+  VQ_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
+                                  const int64_t* labeled, int64_t n_labeled, double* min_d, void* ws,
+                                  size_t ws_bytes, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_x(X, n, d, row_lo, row_hi)) return e;
+  VQ_REQUIRE(min_d != nullptr && n_labeled >= 0, "null min_d");
+  const WsLayout L = ws_layout(n, kMaxRanks);
+  VQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, "workspace too small");
+  char* w = (char*)ws;
+  double* xx = (double*)(w + L.xx);
+  if (int e = fill_f64(min_d + row_lo, row_hi - row_lo, INFINITY, stream)) return e;
+  if (n_labeled == 0) return 0;
+  VQ_REQUIRE(labeled != nullptr, "labeled is null");
+  if (int e = launch_norms(X, n, d, xx, stream)) return e;
+  const int nit = (d / 4 + 31) / 32;
+  const int nbk = max_nbk(nit, kB);
+  for (int64_t c0 = 0; c0 < n_labeled; c0 += nbk) {
+    PassArgs a{};
+    a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.unc = nullptr; a.score = nullptr; a.centers = (const long long*)labeled + c0; a.n_centers = nullptr;
+    a.n_centers_imm = (int)std::min<int64_t>(nbk, n_labeled - c0); a.ctl = nullptr; a.hist = nullptr;
+    if (int e = launch_pass(a, nbk, stream)) return e;
+  }
+  return 0;
+}
+
+extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
+                                    double* min_d, double* unc, int rule, double moks, double lambda,
+                                    int64_t n_labeled, int64_t first_pick, int64_t k, int batch,
+                                    int64_t* out_idx, void* comm_, void* ws, size_t ws_bytes,
+                                    int64_t* host_stats, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_x(X, n, d, row_lo, row_hi)) return e;
+  VQ_REQUIRE(min_d && unc && out_idx, "null pointer");
+  VQ_REQUIRE(rule >= 0 && rule <= 2, "rule must be 0, 1 or 2");
+  VQ_REQUIRE(k >= 0 && k <= n, "k must be in [0, n]");
+  VQ_REQUIRE(batch >= 1, "batch must be >= 1");
+  Comm* comm = (Comm*)comm_;
+  const int world = comm ? comm->world : 1;
+  VQ_REQUIRE(world >= 1 && world <= kMaxRanks, "world size not supported");
+  VQ_REQUIRE(world > 1 || (row_lo == 0 && row_hi == n), "single GPU must own every row");
+  const WsLayout L = ws_layout(n, kMaxRanks);
+  VQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, "workspace too small");
+  if (k == 0) return 0;
+  char* w = (char*)ws;
+  Ctl* ctl = (Ctl*)(w + L.ctl);
+  double* xx = (double*)(w + L.xx);
+  double* score = (double*)(w + L.score);
+  unsigned int* hist = (unsigned int*)(w + L.hist);
+  Best* partial = (Best*)(w + L.partial);
+  RankBlock* send = (RankBlock*)(w + L.send);
+  RankBlock* recv = (world > 1) ? (RankBlock*)(w + L.recv) : send;
+  double* Dcc = (double*)(w + L.dcc);
+  const int nit = (d / 4 + 31) / 32;
+  const int nbk = max_nbk(nit, std::min(batch, kB));
+
+  Ctl h{};
+  h.n_picked = 0; h.k = k; h.nb = 0; h.rule = rule; h.world = world;
+  h.first_round = (n_labeled == 0) ? 1 : 0;
+  h.maxb = nbk;
+  h.wd = (rule == 0) ? (1.0 - moks) : 1.0;
+  h.wu = (rule == 0) ? (lambda * moks) : lambda;
+  h.U = 0.0; h.W = -1.0;
+  if (n_labeled == 0 && rule == 2) {
+    // _query (:828-833): the caller drew the random first pick
+    VQ_REQUIRE(first_pick >= 0 && first_pick < n, "rule 2 with an empty labelled set needs first_pick");
+  }
+  VQ_CUDA(cudaMemcpyAsync(ctl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+  VQ_CUDA(cudaMemsetAsync(hist, 0, (kNB + 1) * 4, stream));
+  VQ_CUDA(cudaMemsetAsync(send, 0, 64, stream));
+  if (int e = launch_norms(X, n, d, xx, stream)) return e;
+
+  const int own = (int)std::min<int64_t>(row_hi - row_lo, 1LL << 30);
+  int fgrid = std::max(1, std::min(sm_count() * 4, (own + 255) / 256));
+  VQ_REQUIRE(fgrid <= 4096, "filter grid too large");
+  const size_t pairs_smem = (size_t)kB * nit * 64 * sizeof(double2);
+  VQ_REQUIRE(pairs_smem <= (size_t)kMaxSmem, "d too large for the candidate kernel");
+  static bool pairs_cfg = false;
+  if (!pairs_cfg) {
+    VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    pairs_cfg = true;
+  }
+
+  if (n_labeled == 0 && rule == 2) {
+    // apply the given first pick directly (one pass), then continue with argmax(min_d)
+    Ctl h2 = h;
+    h2.first_round = 0; h2.n_picked = 1; h2.picks[0] = first_pick; h2.nb = 1;
+    VQ_CUDA(cudaMemcpyAsync(ctl, &h2, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+    VQ_CUDA(cudaMemcpyAsync(out_idx, &first_pick, 8, cudaMemcpyHostToDevice, stream));
+    PassArgs a{};
+    a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl; a.hist = hist;
+    if (int e = launch_pass(a, nbk, stream)) return e;
+  } else {
+    const long long cnt = row_hi - row_lo;
+    if (cnt > 0) {
+      score_init_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(row_lo, row_hi, min_d, unc, score, ctl);
+      VQ_LAUNCHED();
+    }
+  }
+
+  // rounds: filter -> [all-gather] -> pairs -> plan -> pass.  The host only learns the pick
+  // count every `chunk` rounds; kernels of surplus rounds exit on n_picked >= k.
+  long long picked = (n_labeled == 0 && rule == 2) ? 1 : 0;
+  long long rounds_done = 0;
+  long long* h_picked = nullptr;
+  VQ_CUDA(cudaMallocHost(&h_picked, sizeof(Ctl)));
+  int rc = 0;
+  while (picked < k && rc == 0) {
+    const long long remaining = k - picked;
+    double per_round = (rounds_done > 8 && picked > 0) ? (double)picked / (double)rounds_done : (double)std::max(1, nbk / 2);
+    long long chunk = (long long)((double)remaining / std::max(1.0, per_round)) + 2;
+    chunk = std::max<long long>(4, std::min<long long>(chunk, 256));
+    for (long long it = 0; it < chunk && rc == 0; ++it) {
+      filter_kernel<<<fgrid, 256, 0, stream>>>(row_lo, row_hi, min_d, unc, score, hist, partial, send, ctl);
+      g_launches.fetch_add(1);
+      if (world > 1) {
+        const int e = g_nccl.AllGather(send, recv, sizeof(RankBlock), /*ncclChar*/ 0, comm->nccl, stream);
+        if (e != 0) {
+          snprintf(g_err, sizeof(g_err), "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+          rc = VATLQ_ECOMM;
+          break;
+        }
+      }
+      if (nbk > 1) {
+        dim3 pg(kCap / kB, 4);
+        pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, d / 4, nit, xx, recv, ctl, Dcc);
+        g_launches.fetch_add(1);
+      }
+      plan_kernel<<<1, kCap, 0, stream>>>(recv, send, Dcc, (long long*)out_idx, ctl);
+      g_launches.fetch_add(1);
+      PassArgs a{};
+      a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+      a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl;
+      a.hist = (nbk > 1) ? hist : nullptr;
+      rc = launch_pass(a, nbk, stream);
+    }
+    if (rc) break;
+    rounds_done += chunk;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_picked, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "coreset rounds failed: %s", cudaGetErrorString(e));
+      rc = (int)e;
+      break;
+    }
+    const Ctl* hc = (const Ctl*)h_picked;
+    if (hc->n_picked <= picked && hc->n_picked < k) {
+      snprintf(g_err, sizeof(g_err), "coreset made no progress (picked %lld of %lld)", (long long)hc->n_picked, (long long)k);
+      rc = VATLQ_ESTATE;
+      break;
+    }
+    picked = hc->n_picked;
+  }
+  if (rc == 0 && host_stats) {
+    const Ctl* hc = (const Ctl*)h_picked;
+    host_stats[0] = hc->stat_passes;
+    host_stats[1] = hc->n_picked;
+    host_stats[2] = hc->stat_rounds;
+    host_stats[3] = hc->stat_fallback_empty;
+    host_stats[4] = hc->stat_fallback_overflow;
+    host_stats[5] = hc->stat_cand_sum;
+    host_stats[6] = rounds_done;
+    host_stats[7] = nbk;
+  }
+  cudaFreeHost(h_picked);
+  return rc;
+}
+
+extern "C" int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
+                                   double* out, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_x(X, n, d, 0, n)) return e;
+  VQ_REQUIRE(centers && out && m > 0, "null pointer");
+  const int nit = (d / 4 + 31) / 32;
+  const size_t smem = (size_t)kB * nit * 64 * sizeof(double2);
+  VQ_REQUIRE(smem <= (size_t)kMaxSmem, "d too large");
+  static bool cfg = false;
+  if (!cfg) {
+    VQ_CUDA(cudaFuncSetAttribute(pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    cfg = true;
+  }
+  const long long colblocks = (m + kB - 1) / kB;
+  VQ_REQUIRE(colblocks <= 2147483647LL, "too many centers");
+  const int gy = (int)std::max<long long>(1, std::min<long long>(64, (n + 31) / 32));
+  dim3 grid((unsigned)colblocks, (unsigned)gy);
+  pairwise_kernel<<<grid, 256, smem, stream>>>(X, n, d / 4, nit, (const long long*)centers, m, out);
+  VQ_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------- communicator
+extern "C" int vatlq_comm_unique_id(void* host_id128) {
+  VQ_REQUIRE(host_id128 != nullptr, "null id buffer");
+  if (int e = load_nccl()) return e;
+  const int e = g_nccl.GetUniqueId(host_id128);
+  if (e != 0) {
+    snprintf(g_err, sizeof(g_err), "ncclGetUniqueId failed (%d)", e);
+    return VATLQ_ECOMM;
+  }
+  return 0;
+}
+
+extern "C" int vatlq_comm_init(const void* host_id128, int rank, int world, void** comm_out) {
+  VQ_REQUIRE(host_id128 && comm_out && world >= 1 && rank >= 0 && rank < world, "bad arguments");
+  VQ_REQUIRE(world <= kMaxRanks, "world too large");
+  if (int e = load_nccl()) return e;
+  Id128 id;
+  memcpy(id.b, host_id128, 128);
+  void* c = nullptr;
+  const int e = g_nccl.CommInitRank(&c, world, id, rank);
+  if (e != 0) {
+    snprintf(g_err, sizeof(g_err), "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    return VATLQ_ECOMM;
+  }
+  Comm* cm = new Comm{c, rank, world};
+  *comm_out = cm;
+  return 0;
+}
+
+extern "C" int vatlq_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  Comm* cm = (Comm*)comm;
+  if (g_nccl.CommDestroy && cm->nccl) g_nccl.CommDestroy(cm->nccl);
+  delete cm;
+  return 0;
+}

@@ -1,0 +1,136 @@
+"""Multi-GPU plumbing of the query pass: one process per GPU, torch.distributed for the
+rendezvous and the bulk collectives (NCCL over NVLink on GPUs, gloo in the CPU tests), and a
+library-owned NCCL communicator for the per-round candidate exchange inside the core-set loop.
+
+Sharding: rank r owns the contiguous range [r*n/G, (r+1)*n/G) of the id-sorted
+pool.  Heat maps never leave their rank except for one halo frame per side; pooled features are
+all-gathered once (1 M x 2048 fp32 = 8.2 GB, fits every GPU) so that the greedy loop only
+exchanges one small candidate block per round.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+from . import _lib
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced range of rank `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n: int, world: int) -> list[int]:
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def exchange_halo(first: torch.Tensor | None, last: torch.Tensor | None, rank: int, world: int, group=None):
+    """Send this rank's first frame to rank-1 and last frame to rank+1; return
+    (halo_prev, halo_next): the frame before / after the local range (None at the pool ends).
+    Frames are one (J,h,w) tensor = 208 896 B at the reference shape; an empty shard passes
+    the frames it receives through unchanged so that chains of small shards stay correct."""
+    if world == 1:
+        return None, None
+    like = first if first is not None else last
+    if like is None:
+        raise _lib.VatlqError("exchange_halo: empty shards need a template frame")
+    halo_prev = torch.empty_like(like) if rank > 0 else None
+    halo_next = torch.empty_like(like) if rank < world - 1 else None
+    ops_ = []
+    if rank > 0:
+        ops_.append(td.P2POp(td.irecv, halo_prev, _peer(rank - 1, group), group))
+        ops_.append(td.P2POp(td.isend, first.contiguous(), _peer(rank - 1, group), group))
+    if rank < world - 1:
+        ops_.append(td.P2POp(td.isend, last.contiguous(), _peer(rank + 1, group), group))
+        ops_.append(td.P2POp(td.irecv, halo_next, _peer(rank + 1, group), group))
+    for req in td.batch_isend_irecv(ops_):
+        req.wait()
+    return halo_prev, halo_next
+
+
+def _peer(group_rank: int, group):
+    return group_rank if group is None else td.get_global_rank(group, group_rank)
+
+
+def allgather_rows(local: torch.Tensor, n: int, world: int, group=None) -> torch.Tensor:
+    """All-gather row shards of unequal length (shard_range layout) into one (n, ...) tensor."""
+    sizes = shard_sizes(n, world)
+    out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out.copy_(local)
+        return out
+    if len(set(sizes)) == 1:
+        td.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged shards: pad every shard to the longest one, gather, drop the padding
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    buf = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    td.all_gather_into_tensor(buf, pad, group=group)
+    at = 0
+    for r, sz in enumerate(sizes):
+        out[at:at + sz] = buf[r * mx:r * mx + sz]
+        at += sz
+    return out
+
+
+class Comm:
+    """Library-owned NCCL communicator (vatlq_comm_*), bootstrapped through torch.distributed."""
+
+    def __init__(self, group=None):
+        self.rank = td.get_rank(group)
+        self.world = td.get_world_size(group)
+        self.handle = None
+        if self.world == 1:
+            return
+        L = _lib.lib()
+        buf = (C.c_char * 128)()
+        if self.rank == 0:
+            _lib.check(L.vatlq_comm_unique_id(C.cast(buf, C.c_void_p)), "vatlq_comm_unique_id")
+        box = [bytes(buf.raw)]
+        td.broadcast_object_list(box, src=_peer(0, group), group=group)
+        uid = (C.c_char * 128).from_buffer_copy(box[0])
+        out = C.c_void_p()
+        _lib.check(L.vatlq_comm_init(C.cast(uid, C.c_void_p), self.rank, self.world, C.byref(out)), "vatlq_comm_init")
+        self.handle = out.value
+
+    def close(self):
+        if self.handle:
+            _lib.lib().vatlq_comm_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+
+def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_local, ae_weights, labeled_global,
+                      n: int, k: int, moks: float = 0.0, lam: float = 0.01, uncertainty: str = "THC+WPU",
+                      thc_vs_wpu: str = "const", rule: str = "w_unc", batch: int = 8, comm: Comm | None = None,
+                      group=None, first_pick: int = -1):
+    """One query over a pool sharded across the ranks of `group` (one process per GPU).
+    Every rank passes its slice of the pool and gets the same global pick list back."""
+    from . import ops
+    from .query import QueryPass, QueryResult
+    rank, world = td.get_rank(group), td.get_world_size(group)
+    lo, hi = shard_range(n, rank, world)
+    dev = H_local.device
+    qp = QueryPass(hi - lo, dev, ae_weights=ae_weights, uncertainty=uncertainty)
+    hp, hn = exchange_halo(H_local[0] if hi > lo else None, H_local[-1] if hi > lo else None, rank, world, group)
+    qp.score_pool(H_local, boxes_local, is_prev_local, is_next_local, halo_prev=hp, halo_next=hn)
+    lab = np.asarray(list(labeled_global), dtype=np.int64)
+    unl = torch.ones(hi - lo, dtype=torch.uint8, device=dev)
+    mine = lab[(lab >= lo) & (lab < hi)] - lo
+    if mine.size:
+        unl[torch.from_numpy(mine).to(dev)] = 0
+    unc_local = qp.fuse(unl, thc_vs_wpu, labeled_ratio=lab.size / max(n, 1), group=group if world > 1 else None,
+                        n_unlabeled_global=n - lab.size)
+    X = allgather_rows(X_local, n, world, group)
+    unc = allgather_rows(unc_local, n, world, group)
+    picks, st = ops.coreset_select(X, unc, lab, k, moks, lam, rule=rule, batch=batch, first_pick=first_pick,
+                                   comm=comm.handle if comm is not None else None,
+                                   row_range=(lo, hi) if world > 1 else None)
+    return QueryResult(picks=picks, thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts, unc=unc,
+                       combine_weight=qp.combine_weight, stats=st)

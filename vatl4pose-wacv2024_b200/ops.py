@@ -1,0 +1,257 @@
+"""Batched device operators of the query pass: thin torch-tensor wrappers over the C ABI.
+
+Every function takes CUDA tensors (borrowed pointers go straight into libvatlq), launches on
+torch's current stream and returns CUDA tensors.  Nothing here computes on the CPU and nothing
+falls back: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+J, HM_H, HM_W = 17, 64, 48
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.VatlqError(f"{name} must be a CUDA tensor (the query pass has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.VatlqError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _flags(t, n: int, dev, name: str):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    t = t.to(device=dev).to(torch.uint8).contiguous()
+    if t.numel() != n:
+        raise _lib.VatlqError(f"{name} must have {n} entries")
+    return t
+
+
+@dataclass
+class ScanResult:
+    thc: torch.Tensor        # (n,) fp32
+    peak_sum: torch.Tensor   # (n,) fp32
+    peak_cnt: torch.Tensor   # (n,) int32
+    peak_mean: torch.Tensor  # (n,) fp32 (NaN where no peak survives)
+    coords_hm: torch.Tensor  # (n,J,2) fp32 heat-map-space coordinates
+    kpts: torch.Tensor | None  # (n,J,3) fp32 image-space x, y, score (needs boxes)
+
+
+def heatmap_scan(H: torch.Tensor, is_prev=None, is_next=None, boxes_xyxy: torch.Tensor | None = None,
+                 halo_prev: torch.Tensor | None = None, halo_next: torch.Tensor | None = None) -> ScanResult:
+    """THC + local-peak statistics + argmax/quarter-pixel coordinates of a whole pool in one pass
+    (vatlq_heatmap_scan).  H (n,J,h,w) fp32 CUDA; flags length n; boxes (n,4) fp32 xyxy."""
+    H = _cuda(H, torch.float32, "H")
+    if H.dim() != 4:
+        raise _lib.VatlqError("H must be (n,J,h,w)")
+    n, nj, h, w = H.shape
+    dev = H.device
+    ip = _flags(is_prev, n, dev, "is_prev")
+    inx = _flags(is_next, n, dev, "is_next")
+    bb = None if boxes_xyxy is None else _cuda(boxes_xyxy.to(dev), torch.float32, "boxes_xyxy")
+    if bb is not None and tuple(bb.shape) != (n, 4):
+        raise _lib.VatlqError("boxes_xyxy must be (n,4)")
+    hp = None if halo_prev is None else _cuda(halo_prev, torch.float32, "halo_prev")
+    hn = None if halo_next is None else _cuda(halo_next, torch.float32, "halo_next")
+    for t, nm in ((hp, "halo_prev"), (hn, "halo_next")):
+        if t is not None and t.numel() != nj * h * w:
+            raise _lib.VatlqError(f"{nm} must be one (J,h,w) frame")
+    L = _lib.lib()
+    ws_bytes = L.vatlq_heatmap_scan_workspace_bytes(n, nj)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    out = ScanResult(
+        thc=torch.empty(n, dtype=torch.float32, device=dev),
+        peak_sum=torch.empty(n, dtype=torch.float32, device=dev),
+        peak_cnt=torch.empty(n, dtype=torch.int32, device=dev),
+        peak_mean=torch.empty(n, dtype=torch.float32, device=dev),
+        coords_hm=torch.empty((n, nj, 2), dtype=torch.float32, device=dev),
+        kpts=None if bb is None else torch.empty((n, nj, 3), dtype=torch.float32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(L.vatlq_heatmap_scan(_ptr(H), _ptr(ip), _ptr(inx), n, nj, h, w, _ptr(hp), _ptr(hn), _ptr(bb),
+                                        _ptr(out.thc), _ptr(out.peak_sum), _ptr(out.peak_cnt), _ptr(out.peak_mean),
+                                        _ptr(out.coords_hm), _ptr(out.kpts), _ptr(ws), ws_bytes, _stream()),
+                   "vatlq_heatmap_scan")
+    return out
+
+
+def thc3(cur: torch.Tensor, prev: torch.Tensor | None, nxt: torch.Tensor | None, is_prev, is_next) -> torch.Tensor:
+    """Strict three-tensor THC (separately forwarded prev/next crops, ActiveLearning.py:293-297)."""
+    cur = _cuda(cur, torch.float32, "cur")
+    n, nj, h, w = cur.shape
+    dev = cur.device
+    prev = None if prev is None else _cuda(prev, torch.float32, "prev")
+    nxt = None if nxt is None else _cuda(nxt, torch.float32, "next")
+    ip = _flags(is_prev, n, dev, "is_prev")
+    inx = _flags(is_next, n, dev, "is_next")
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vatlq_thc3(_ptr(cur), _ptr(prev), _ptr(nxt), _ptr(ip), _ptr(inx), n, nj, h, w,
+                                         _ptr(out), _stream()), "vatlq_thc3")
+    return out
+
+
+def pack_ae_weights(weights, device) -> tuple[torch.Tensor, int, int]:
+    """Pack the 8 Linear layers of a WholeBodyAE into the flat layout vatlq_wpu expects.
+    `weights`: a state_dict (encoder.{0,2,4,6}/decoder.{0,2,4,6}.{weight,bias}), an nn.Module
+    with .state_dict(), or a list of 8 (W[out,in], b[out]) pairs."""
+    if hasattr(weights, "state_dict"):
+        weights = weights.state_dict()
+    if isinstance(weights, dict):
+        pairs = []
+        for part in ("encoder", "decoder"):
+            for k in (0, 2, 4, 6):
+                pairs.append((weights[f"{part}.{k}.weight"], weights[f"{part}.{k}.bias"]))
+    else:
+        pairs = list(weights)
+    if len(pairs) != 8:
+        raise _lib.VatlqError("WholeBodyAE has 8 Linear layers")
+    flat = []
+    for Wm, b in pairs:
+        Wm = torch.as_tensor(np.asarray(Wm) if not isinstance(Wm, torch.Tensor) else Wm).detach().float().cpu()
+        b = torch.as_tensor(np.asarray(b) if not isinstance(b, torch.Tensor) else b).detach().float().cpu()
+        flat += [Wm.reshape(-1), b.reshape(-1)]
+    in_dim = int(pairs[0][0].shape[1])
+    z_dim = int(pairs[3][0].shape[0])
+    dims = [in_dim, 24, 12, 7, z_dim, 7, 12, 24, in_dim]
+    for (Wm, _), a, b in zip(pairs, dims[:-1], dims[1:]):
+        if tuple(Wm.shape) != (b, a):
+            raise _lib.VatlqError(f"unexpected AE layer shape {tuple(Wm.shape)}, wanted {(b, a)}")
+    packed = torch.cat(flat).contiguous().to(device)
+    assert packed.numel() == _lib.lib().vatlq_wpu_weight_count(in_dim, z_dim)
+    return packed, in_dim, z_dim
+
+
+def wpu(kpts: torch.Tensor, boxes_xyxy: torch.Tensor, packed_weights: torch.Tensor, in_dim: int, z_dim: int,
+        drop_ears: bool = False, return_features: bool = False, check_status: bool = True):
+    """Whole-body pose unnaturalness of every pose (vatlq_wpu).  kpts (n,17,3) fp32 CUDA."""
+    kpts = _cuda(kpts, torch.float32, "kpts")
+    n = kpts.shape[0]
+    if kpts.numel() != n * 51:
+        raise _lib.VatlqError("kpts must be (n,17,3)")
+    dev = kpts.device
+    bb = _cuda(boxes_xyxy.to(dev), torch.float32, "boxes_xyxy")
+    wts = _cuda(packed_weights, torch.float32, "weights")
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    feat = torch.empty((n, in_dim), dtype=torch.float32, device=dev) if return_features else None
+    status = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vatlq_wpu(_ptr(kpts), _ptr(bb), _ptr(wts), in_dim, z_dim, int(drop_ears), _ptr(out),
+                                        _ptr(feat), _ptr(status), n, _stream()), "vatlq_wpu")
+    if check_status:
+        bad = int(status.max().item()) if n else 0
+        if bad:  # the reference's AssertionErrors (hybrid_feature.py:25,31)
+            raise AssertionError("height of human body must be positive!" if bad == 1
+                                 else "at least one visible keypoint is required!")
+    return (out, feat) if return_features else out
+
+
+FUSE_MODES = {"const": 0, "increase": 1, "decrease": 2, "single": 3}
+
+
+def fuse_scores(thc: torch.Tensor, wpu_: torch.Tensor | None, unlabeled: torch.Tensor | None,
+                mode: str = "const", labeled_ratio: float = 0.0, group=None) -> torch.Tensor:
+    """Min-max / combine / min-max of ActiveLearning.py:490-516 on the device, float64.
+    Returns unc (n,) fp64 with 0 at labelled rows.  `group`: a torch.distributed group whose
+    ranks hold disjoint shards of the pool (statistics are all-reduced with MIN)."""
+    thc = _cuda(thc, torch.float32, "thc")
+    n = thc.numel()
+    dev = thc.device
+    w = None if wpu_ is None else _cuda(wpu_, torch.float32, "wpu")
+    m = FUSE_MODES["single"] if w is None else FUSE_MODES[mode]
+    unl = _flags(unlabeled, n, dev, "unlabeled")
+    L = _lib.lib()
+    s1 = torch.empty(4, dtype=torch.float64, device=dev)
+    s2 = torch.empty(2, dtype=torch.float64, device=dev)
+    u = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.vatlq_fuse_stats(_ptr(thc), _ptr(w), _ptr(unl), n, _ptr(s1), _stream()), "vatlq_fuse_stats")
+        if group is not None:
+            torch.distributed.all_reduce(s1, op=torch.distributed.ReduceOp.MIN, group=group)
+        _lib.check(L.vatlq_fuse_combine(_ptr(thc), _ptr(w), _ptr(unl), n, _ptr(s1), m, float(labeled_ratio),
+                                        _ptr(u), _ptr(s2), _stream()), "vatlq_fuse_combine")
+        if group is not None:
+            torch.distributed.all_reduce(s2, op=torch.distributed.ReduceOp.MIN, group=group)
+        _lib.check(L.vatlq_fuse_final(_ptr(unl), n, _ptr(s2), _ptr(u), _stream()), "vatlq_fuse_final")
+    return u
+
+
+RULES = {"w_unc": 0, "fixed_lambda": 1, "dist": 2}
+
+
+@dataclass
+class CoresetStats:
+    passes: int
+    picks: int
+    rounds: int
+    fallback_empty: int
+    fallback_overflow: int
+    candidates: int
+    rounds_launched: int
+    batch: int
+
+
+def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: float, lam: float,
+                   rule: str = "w_unc", first_pick: int = -1, batch: int = 8, comm=None,
+                   row_range: tuple[int, int] | None = None, return_state: bool = False):
+    """k-center greedy selection (vatlq_coreset_init + vatlq_coreset_select).
+    X (n,d) fp32 CUDA (replicated on every rank when comm is given), unc (n,) fp64 CUDA — a
+    private copy is made, like the caller's deepcopy at ActiveLearning.py:612-613.
+    Returns the picks as an int64 CUDA tensor in pick order (and stats / min_d / unc)."""
+    X = _cuda(X, torch.float32, "X")
+    n, d = X.shape
+    dev = X.device
+    unc = _cuda(unc, torch.float64, "unc").clone()
+    if unc.numel() != n:
+        raise _lib.VatlqError("unc must have n entries")
+    lab = torch.as_tensor(np.asarray(list(labeled) if not isinstance(labeled, (np.ndarray, torch.Tensor)) else
+                                     (labeled.cpu().numpy() if isinstance(labeled, torch.Tensor) else labeled),
+                                     dtype=np.int64)).to(dev)
+    lo, hi = (0, n) if row_range is None else row_range
+    L = _lib.lib()
+    ws_bytes = L.vatlq_coreset_workspace_bytes(n, d, batch)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    min_d = torch.empty(n, dtype=torch.float64, device=dev)
+    out = torch.empty(max(k, 1), dtype=torch.int64, device=dev)
+    stats = (C.c_int64 * 8)()
+    with torch.cuda.device(dev):
+        _lib.check(L.vatlq_coreset_init(_ptr(X), n, d, lo, hi, _ptr(lab) if lab.numel() else None, lab.numel(),
+                                        _ptr(min_d), _ptr(ws), ws_bytes, _stream()), "vatlq_coreset_init")
+        _lib.check(L.vatlq_coreset_select(_ptr(X), n, d, lo, hi, _ptr(min_d), _ptr(unc), RULES[rule], float(moks),
+                                          float(lam), lab.numel(), int(first_pick), int(k), int(batch), _ptr(out),
+                                          C.c_void_p(comm) if comm else None, _ptr(ws), ws_bytes,
+                                          C.cast(stats, C.c_void_p), _stream()), "vatlq_coreset_select")
+    picks = out[:k]
+    st = CoresetStats(*[int(v) for v in stats])
+    if return_state:
+        return picks, st, min_d, unc
+    return picks, st
+
+
+def pairwise_dist(X: torch.Tensor, centers) -> torch.Tensor:
+    """(n,m) fp64 Euclidean distances of every row to X[centers] with the library's canonical
+    fp64 arithmetic (sklearn order: sqrt(max(0, -2 x.c + |x|^2 + |c|^2)))."""
+    X = _cuda(X, torch.float32, "X")
+    n, d = X.shape
+    c = torch.as_tensor(np.asarray(centers, dtype=np.int64)).to(X.device)
+    out = torch.empty((n, c.numel()), dtype=torch.float64, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.lib().vatlq_pairwise_dist(_ptr(X), n, d, _ptr(c), c.numel(), _ptr(out), _stream()),
+                   "vatlq_pairwise_dist")
+    return out

@@ -154,6 +154,13 @@ int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64
 int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
                         double* out, vatlq_stream_t stream);
 
+/* Timing of the dominant kernel (the pass over X) for bench.py's roofline: when enabled,
+ * vatlq_coreset_select brackets every pass launch with CUDA events on `stream`; read returns
+ * the summed duration of the passes that applied picks, their number and the picks applied.
+ * The picks counter only covers chunks of rounds that were timed from their first launch. */
+int vatlq_profile_passes(int enable);
+int vatlq_profile_read(double* host_total_ms, int64_t* host_launches, int64_t* host_picks, int reset);
+
 /* ------------------------------------------------------------------------------------
  * NCCL plumbing for the multi-GPU argmax exchange (one process per GPU).  NCCL is
  * dlopen()ed (libnccl.so.2, the copy torch already loaded); absent -> VATLQ_ECOMM.

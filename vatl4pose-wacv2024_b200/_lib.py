@@ -29,6 +29,8 @@ SIGNATURES = {
     "vatlq_coreset_select": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _dbl, _dbl, _i64,
                                     _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vatlq_pairwise_dist": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp]),
+    "vatlq_profile_passes": (_int, [_int]),
+    "vatlq_profile_read": (_int, [_vp, _vp, _vp, _int]),
     "vatlq_comm_unique_id": (_int, [_vp]),
     "vatlq_comm_init": (_int, [_vp, _int, _int, C.POINTER(_vp)]),
     "vatlq_comm_destroy": (_int, [_vp]),

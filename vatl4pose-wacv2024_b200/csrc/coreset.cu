@@ -14,6 +14,10 @@
 // kB picks at once, reading every row of X from HBM once instead of kB times.
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <vector>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vatlq {
@@ -758,6 +762,17 @@ static WsLayout ws_layout(long long n, int world) {
   return L;
 }
 
+// ---------------------------------------------------------------- pass-kernel timing (bench.py roofline)
+struct PassProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // start/stop pairs
+  size_t used = 0;
+  double total_ms = 0.0;         // summed duration of real passes (nb > 0)
+  long long timed = 0;           // how many real passes were timed
+  long long picks = 0;           // picks those passes applied
+};
+static PassProfiler g_prof;
+
 }  // namespace vatlq
 
 using namespace vatlq;
@@ -916,6 +931,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   // count every `chunk` rounds; kernels of surplus rounds exit on n_picked >= k.
   long long picked = (n_labeled == 0 && rule == 2) ? 1 : 0;
   long long rounds_done = 0;
+  long long passes_seen = (n_labeled == 0 && rule == 2) ? 1 : 0;
+  g_prof.used = 0;
   long long* h_picked = nullptr;
   VQ_CUDA(cudaMallocHost(&h_picked, sizeof(Ctl)));
   int rc = 0;
@@ -946,7 +963,13 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
       a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl;
       a.hist = (nbk > 1) ? hist : nullptr;
+      const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+      if (timed) cudaEventRecord(g_prof.ev[g_prof.used], stream);
       rc = launch_pass(a, nbk, stream);
+      if (timed) {
+        cudaEventRecord(g_prof.ev[g_prof.used + 1], stream);
+        g_prof.used += 2;
+      }
     }
     if (rc) break;
     rounds_done += chunk;
@@ -959,6 +982,21 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       break;
     }
     const Ctl* hc = (const Ctl*)h_picked;
+    if (g_prof.on) {
+      // only the first (stat_passes - passes_seen) launches of this chunk did work; later ones
+      // found nb == 0 (all picks made) and returned at once
+      const long long real = std::min<long long>(hc->stat_passes - passes_seen, (long long)(g_prof.used / 2));
+      for (long long i = 0; i < real; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
+          g_prof.total_ms += ms;
+          g_prof.timed += 1;
+        }
+      }
+      g_prof.picks += hc->n_picked - picked;
+      g_prof.used = 0;
+    }
+    passes_seen = hc->stat_passes;
     if (hc->n_picked <= picked && hc->n_picked < k) {
       snprintf(g_err, sizeof(g_err), "coreset made no progress (picked %lld of %lld)", (long long)hc->n_picked, (long long)k);
       rc = VATLQ_ESTATE;
@@ -1037,5 +1075,27 @@ extern "C" int vatlq_comm_destroy(void* comm) {
   Comm* cm = (Comm*)comm;
   if (g_nccl.CommDestroy && cm->nccl) g_nccl.CommDestroy(cm->nccl);
   delete cm;
+  return 0;
+}
+
+// ---------------------------------------------------------------- profiling hooks
+extern "C" int vatlq_profile_passes(int enable) {
+  if (enable && g_prof.ev.empty()) {
+    g_prof.ev.resize(2 * 8192);
+    for (auto& e : g_prof.ev) VQ_CUDA(cudaEventCreate(&e));
+  }
+  g_prof.on = enable != 0;
+  return 0;
+}
+
+extern "C" int vatlq_profile_read(double* total_ms, int64_t* launches, int64_t* picks, int reset) {
+  if (total_ms) *total_ms = g_prof.total_ms;
+  if (launches) *launches = g_prof.timed;
+  if (picks) *picks = g_prof.picks;
+  if (reset) {
+    g_prof.total_ms = 0.0;
+    g_prof.timed = 0;
+    g_prof.picks = 0;
+  }
   return 0;
 }

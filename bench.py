@@ -153,8 +153,6 @@ def main():
             return
         import torch  # noqa: F401
         vals = []
-        for _ in range(max(a.warmup, 0) and 0):
-            pass
         det = None
         for _ in range(max(1, min(a.steps, 3))):
             v, det = cpu_reference_arm(n, k, moks, lam, a.cpu_frames, a.cpu_greedy_steps)

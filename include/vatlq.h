@@ -152,7 +152,7 @@ int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64
 /* One pairwise-distance column block, exposed for parity tests of the distance arithmetic:
  * out[i*m + j] = d(X[i], X[centers[j]]) in fp64 (sklearn _euclidean_distances order). */
 int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
-                        double* out, vatlq_stream_t stream);
+                        double* out, void* ws /* >= n*8 bytes */, size_t ws_bytes, vatlq_stream_t stream);
 
 /* Timing of the dominant kernel (the pass over X) for bench.py's roofline: when enabled,
  * vatlq_coreset_select brackets every pass launch with CUDA events on `stream`; read returns

@@ -17,7 +17,8 @@ def test_golden_coreset(built_lib, gold_coreset, batch):
             torch.from_numpy(c["X"]).cuda(), torch.from_numpy(c["unc"]).cuda(), labeled, int(c["k"]),
             float(c["moks"]), float(c["lam"]), rule=str(c["rule"]), first_pick=first, batch=batch, return_state=True)
         assert picks.cpu().tolist() == c["picks"].tolist(), (tag, batch)
-        assert np.allclose(md.cpu().numpy(), c["min_d"], rtol=1e-5, atol=1e-9), tag
+        # the reference's d(c,c) is ~1e-8 (BLAS dot vs einsum norms), ours is exactly 0
+        assert np.allclose(md.cpu().numpy(), c["min_d"], rtol=1e-5, atol=1e-6), tag
         assert (unc_after.cpu().numpy()[c["picks"]] == 0).all()
         assert st.picks == int(c["k"]) and st.passes >= 1
         if batch == 8 and int(c["k"]) >= 40:

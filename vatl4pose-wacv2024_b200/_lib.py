@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvatlq.so")
+LIB_PATH = os.environ.get("VATLQ_LIB") or os.path.join(HERE, "libvatlq.so")   # VATLQ_LIB: tuning builds only
 
 _vp, _i64, _int, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
 
@@ -28,7 +28,7 @@ SIGNATURES = {
     "vatlq_coreset_init": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vatlq_coreset_select": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _dbl, _dbl, _i64,
                                     _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "vatlq_pairwise_dist": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp]),
+    "vatlq_pairwise_dist": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vatlq_profile_passes": (_int, [_int]),
     "vatlq_profile_read": (_int, [_vp, _vp, _vp, _int]),
     "vatlq_comm_unique_id": (_int, [_vp]),

@@ -1,10 +1,10 @@
 // k-center greedy core-set selection (ActiveLearning.coreset_selection,
 // active_learning/ActiveLearning.py:798-850) with fp64 distance arithmetic on fp32 features.
 //
-// One canonical distance d(i,c) is used everywhere (same summation order in every kernel):
-//   dot(i,c): lane l of a warp accumulates the float4 chunks q = l, l+32, ... of the rows with
-//             an fp64 FMA chain (products of fp32 values are exact in fp64), then a fixed xor
-//             butterfly adds the 32 partials;
+// One canonical distance d(i,c) is used everywhere (the same instruction sequence in every
+// kernel, see "the fp64 tensor-core tile" below):
+//   dot(i,c): fp64 tensor-core MMAs (mma.sync.m8n8k4.f64) over the features in a fixed order,
+//             fp32 inputs widened exactly, fp64 accumulation;
 //   d(i,c) = sqrt(max(0, (-2*dot + xx_i) + xx_c))   (sklearn _euclidean_distances order).
 //
 // Exact batching: scores only ever decrease, so the next greedy picks
@@ -23,14 +23,16 @@
 namespace vatlq {
 
 constexpr int kB = 8;        // picks applied per pass over X
-constexpr int kR = 4;        // rows per warp step (register tile kR x kB)
-constexpr int kPassThreads = 256;
+#ifndef VQ_PASS_THREADS
+#define VQ_PASS_THREADS 512
+#endif
+constexpr int kPassThreads = VQ_PASS_THREADS;
 constexpr int kCapL = 1024;  // candidate records per rank
 constexpr int kCap = 1024;   // candidates the planner handles (one per thread)
 constexpr int kNB = 1024;    // score-histogram bins
 constexpr int kTarget = 256; // wanted candidates per round (all ranks together)
 constexpr int kMaxRanks = 16;
-constexpr int kMaxSmem = 200 * 1024;
+constexpr int kMaxSmem = 220 * 1024;
 
 struct RankBlock {  // the all-gather unit: one per rank per round
   long long count;  // rows with score >= theta (records beyond kCapL are dropped -> overflow)
@@ -91,76 +93,134 @@ __device__ __forceinline__ double dist_from_dot(double dot, double xxi, double x
   return sqrt(fmax(t, 0.0));
 }
 
-// ---- candidate rows in shared memory: fp64, laid out so that lane l's chunk of iteration
-// `it` is two conflict-free double2 loads: s_c[((j*nit + it)*2 + half)*32 + l]
-__device__ __forceinline__ void stage_center(const float* __restrict__ X, int d4, int nit, long long row, int j,
-                                             double2* s_c) {
+// ---- the fp64 tensor-core tile --------------------------------------------------------------
+// mma.sync.m8n8k4.f64 (DMMA; measured 18.5 T FMA/s on B200, tools/micro/fp64_rate.cu): a warp
+// computes 8 rows x 8 centers per instruction with ONE A and ONE B operand per lane, so the
+// register tile is tiny (2 doubles per 8x8 block) and shared-memory traffic is 1/8 of a scalar
+// DFMA register tile.  Lane (g = lane>>2, kk = lane&3) owns row g of an 8-row block and feeds,
+// for super-step s (16 features), the float4 x[row][16s+4kk .. +3]; element e of that float4
+// is k-slot kk of MMA e, i.e. feature 16s+4kk+e.  The B operand of lane (g, kk) is center g
+// at the same feature.  Output: lane holds (row g, centers 2kk and 2kk+1).
+//
+// CANONICAL DOT: the feature axis is cut into kSeg = 4 segments of ceil(nss/4) super-steps.
+// Inside a segment, element e (0..3) of every float4 feeds its own sequential DMMA chain
+// (four independent chains hide the ~130-cycle dependent-issue latency of DMMA), and
+//   P_seg = (c_0 + c_1) + (c_2 + c_3),     dot = (P0 + P1) + (P2 + P3).
+// Every kernel (norms, pass, candidate pairs, pairwise) evaluates exactly this, so d(i,c) has
+// the same bits wherever it is computed and dot(x,x) == xx (d(c,c) == 0).  In the pass the four
+// segments of a block are computed by the four warps of a "team" in parallel (split-K), which
+// keeps all 16 warps of an SM busy even when a rank owns only ~20 k rows.
+constexpr int kSeg = 4;
+#ifndef VQ_DEPTH
+#define VQ_DEPTH 8
+#endif
+constexpr int kDepth = VQ_DEPTH;     // super-steps of x in flight per lane (register ring)
+#ifndef VQ_PREFETCH
+#define VQ_PREFETCH 0
+#endif
+constexpr int kPrefetch = VQ_PREFETCH;  // super-steps the L2 prefetch cursor runs ahead of the ring
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// centers in shared memory: fp64, row stride S = dpad + 2 doubles (== 16 bytes mod 128, which
+// makes the two 16-byte B loads of a quarter-warp conflict free), features >= d zero
+__device__ __forceinline__ void stage_center(const float* __restrict__ X, int d4, int dpad, int S, long long row, int j,
+                                             double* s_c) {
   const float4* src = reinterpret_cast<const float4*>(X) + (size_t)row * d4;
-  for (int q = threadIdx.x; q < nit * 32; q += blockDim.x) {
+  for (int q = threadIdx.x; q < dpad / 4; q += blockDim.x) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < d4) v = __ldg(src + q);
-    const int base = ((j * nit + (q >> 5)) * 2) * 32 + (q & 31);
-    s_c[base] = make_double2((double)v.x, (double)v.y);
-    s_c[base + 32] = make_double2((double)v.z, (double)v.w);
+    double2* dst = reinterpret_cast<double2*>(s_c + (size_t)j * S + 4 * q);
+    dst[0] = make_double2((double)v.x, (double)v.y);
+    dst[1] = make_double2((double)v.z, (double)v.w);
   }
 }
 
-// canonical dot products of kR rows against NBK staged centers; every lane ends with all sums
-template <int NBK>
-__device__ __forceinline__ void dot_tile(const float4* const (&rowp)[kR], int d4, int nit, const double2* __restrict__ s_c,
-                                         int lane, double (&acc)[kR][NBK]) {
+// x[row][4q..4q+3]; GUARD only when d is not a multiple of 16 (the last super-step is ragged)
+template <bool GUARD>
+__device__ __forceinline__ float4 load_x(const float4* p, int q, int d4) {
+  if (GUARD && q >= d4) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return ldg_stream(p + q);
+}
+
+__device__ __forceinline__ void dmma_step(double (&c)[4][2], const float4& x, const double* bp) {
+  const double2 b01 = *reinterpret_cast<const double2*>(bp);
+  const double2 b23 = *reinterpret_cast<const double2*>(bp + 2);
+  const double x0 = (double)x.x, x1 = (double)x.y, x2 = (double)x.z, x3 = (double)x.w;
+  dmma(c[0], x0, b01.x);
+  dmma(c[1], x1, b01.y);
+  dmma(c[2], x2, b23.x);
+  dmma(c[3], x3, b23.y);
+}
+__device__ __forceinline__ void dmma_step_self(double (&c)[4][2], const float4& x) {
+  const double x0 = (double)x.x, x1 = (double)x.y, x2 = (double)x.z, x3 = (double)x.w;
+  dmma(c[0], x0, x0);
+  dmma(c[1], x1, x1);
+  dmma(c[2], x2, x2);
+  dmma(c[3], x3, x3);
+}
+
+__device__ __forceinline__ double combine4(double p0, double p1, double p2, double p3) {
+  return __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
+}
+
+// canonical dots of one 8-row block (this lane's row pointer `rowp`, never null) against the 8
+// staged centers, all four segments by one warp (four independent chains): used by the small
+// kernels.  self != 0: B = A (row norms, no shared memory).
+template <bool GUARD, bool SELF>
+__device__ __forceinline__ void dmma_block(const float4* rowp, int d4, int nss, const double* __restrict__ s_c, int S,
+                                           int lane, double (&out)[2]) {
+  const int g = lane >> 2, kk = lane & 3;
+  const int seglen = (nss + kSeg - 1) / kSeg;
+  const double* bptr = SELF ? nullptr : s_c + (size_t)g * S + 4 * kk;
+  double c[kSeg][4][2];
 #pragma unroll
-  for (int r = 0; r < kR; ++r)
+  for (int q = 0; q < kSeg; ++q)
 #pragma unroll
-    for (int j = 0; j < NBK; ++j) acc[r][j] = 0.0;
-#pragma unroll 2
-  for (int it = 0; it < nit; ++it) {
-    const int q = it * 32 + lane;
-    float4 xv[kR];
+    for (int e = 0; e < 4; ++e) c[q][e][0] = c[q][e][1] = 0.0;
+  for (int s = 0; s < seglen; ++s) {
+    float4 x[kSeg];
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rowp[r] != nullptr && q < d4) xv[r] = ldg_stream(rowp[r] + q);
+    for (int q = 0; q < kSeg; ++q) {
+      const int ss = q * seglen + s;
+      x[q] = (ss < nss) ? load_x<GUARD>(rowp, 4 * ss + kk, d4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < NBK; ++j) {
-      const double2 c01 = s_c[((j * nit + it) * 2) * 32 + lane];
-      const double2 c23 = s_c[((j * nit + it) * 2 + 1) * 32 + lane];
-#pragma unroll
-      for (int r = 0; r < kR; ++r) {
-        double a = acc[r][j];
-        a = fma((double)xv[r].x, c01.x, a);
-        a = fma((double)xv[r].y, c01.y, a);
-        a = fma((double)xv[r].z, c23.x, a);
-        a = fma((double)xv[r].w, c23.y, a);
-        acc[r][j] = a;
+    for (int q = 0; q < kSeg; ++q) {
+      const int ss = q * seglen + s;
+      if (ss < nss) {
+        if (SELF) dmma_step_self(c[q], x[q]);
+        else dmma_step(c[q], x[q], bptr + 16 * ss);
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < kR; ++r)
+  for (int h = 0; h < 2; ++h) {
+    double p[kSeg];
 #pragma unroll
-    for (int j = 0; j < NBK; ++j) acc[r][j] = warp_sum(acc[r][j]);
+    for (int q = 0; q < kSeg; ++q) p[q] = combine4(c[q][0][h], c[q][1][h], c[q][2][h], c[q][3][h]);
+    out[h] = combine4(p[0], p[1], p[2], p[3]);
+  }
 }
 
 // ---------------------------------------------------------------- squared row norms
-__global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ X, long long n, int d4,
+// xx_i = dot(x_i, x_i): in the diagonal 8x8 block the B operand of lane (g,kk) is its own A
+// operand; the diagonal element (g,g) lives in lane (g, g>>1), slot g&1.
+template <bool GUARD>
+__global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ X, long long n, int d4, int nss,
                                                         double* __restrict__ xx) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long i = w; i < n; i += nw) {
-    const float4* p = reinterpret_cast<const float4*>(X) + (size_t)i * d4;
-    double a = 0.0;
-    for (int q = lane; q < d4; q += 32) {
-      const float4 v = ldg_stream(p + q);
-      a = fma((double)v.x, (double)v.x, a);
-      a = fma((double)v.y, (double)v.y, a);
-      a = fma((double)v.z, (double)v.z, a);
-      a = fma((double)v.w, (double)v.w, a);
-    }
-    a = warp_sum(a);
-    if (lane == 0) xx[i] = a;
+  for (long long r0 = w * 8; r0 < n; r0 += nw * 8) {
+    const long long row = min(r0 + g, n - 1);
+    double c[2];
+    dmma_block<GUARD, true>(reinterpret_cast<const float4*>(X) + (size_t)row * d4, d4, nss, nullptr, 0, lane, c);
+    if (kk == (g >> 1) && r0 + g < n) xx[r0 + g] = (g & 1) ? c[1] : c[0];
   }
 }
 
@@ -168,7 +228,7 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict_
 struct PassArgs {
   const float* X;
   long long n;
-  int d4, nit;
+  int d4, nss, S;
   long long lo, hi;          // owned rows
   const double* xx;
   double* m;
@@ -181,22 +241,33 @@ struct PassArgs {
   unsigned int* hist;        // null: no histogram
 };
 
-template <int NBK>
-__device__ __forceinline__ void pass_body(const PassArgs& a, int nb, double2* s_c, double* s_xxc, long long* s_pick,
-                                          unsigned int* s_hist) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int j = 0; j < NBK; ++j) {
-    const long long p = a.centers[min(j, nb - 1)];  // pad with the last pick: min() is idempotent
-    stage_center(a.X, a.d4, a.nit, p, j, s_c);
+constexpr int kTeams = kPassThreads / 32 / kSeg;   // 4 teams of 4 warps
+
+template <bool GUARD>
+__global__ void __launch_bounds__(kPassThreads, 1) pass_kernel(PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  if (nb <= 0) return;
+  double* s_c = reinterpret_cast<double*>(smem_raw);
+  double* s_xxc = s_c + (size_t)kB * a.S;
+  double* s_part = s_xxc + kB;                               // [team][buf][seg][64]
+  long long* s_pick = reinterpret_cast<long long*>(s_part + kTeams * 2 * kSeg * 64);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
+  const int team = warp >> 2, seg = warp & 3;
+  const int dpad = a.nss * 16;
+  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  for (int j = 0; j < kB; ++j) {
+    const long long p = a.centers[min(j, nb - 1)];  // pad with the last center: min() is idempotent
+    stage_center(a.X, a.d4, dpad, a.S, p, j, s_c);
     if (threadIdx.x == 0) {
       s_xxc[j] = a.xx[p];
       s_pick[j] = p;
     }
   }
   const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
-  double h_lo = 0.0, h_inv = 0.0;
+  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
   int rule = 0;
-  double wd = 0.0, wu = 0.0;
   if (a.ctl) {
     rule = a.ctl->rule;
     wd = a.ctl->wd;
@@ -208,28 +279,45 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, int nb, double2* s_
     }
   }
   __syncthreads();
+
   const float4* X4 = reinterpret_cast<const float4*>(a.X);
-  const long long stride = (long long)gridDim.x * nwarp * kR;
-  for (long long g = a.lo + ((long long)blockIdx.x * nwarp + warp) * kR; g < a.hi; g += stride) {
-    const float4* rowp[kR];
-#pragma unroll
-    for (int r = 0; r < kR; ++r) rowp[r] = (g + r < a.hi) ? X4 + (size_t)(g + r) * a.d4 : nullptr;
-    double acc[kR][NBK];
-    dot_tile<NBK>(rowp, a.d4, a.nit, s_c, lane, acc);
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      if (lane == r && g + r < a.hi) {
-        const long long i = g + r;
-        const double xxi = a.xx[i];
-        double dmin = a.m[i];
-        bool picked = false;
-#pragma unroll
-        for (int j = 0; j < NBK; ++j) {
-          dmin = fmin(dmin, dist_from_dot(acc[r][j], xxi, s_xxc[j]));
-          picked = picked || (s_pick[j] == i);
-        }
+  const long long ntiles = (a.hi - a.lo + 7) / 8;
+  const long long t0 = (long long)blockIdx.x * kTeams + team, tstride = (long long)gridDim.x * kTeams;
+  const long long nt = (t0 < ntiles) ? (ntiles - t0 + tstride - 1) / tstride : 0;
+  const int seglen = (a.nss + kSeg - 1) / kSeg;
+  const int seg_beg = min(a.nss, seg * seglen), seg_end = min(a.nss, seg_beg + seglen), mylen = seg_end - seg_beg;
+  const double* bptr = s_c + (size_t)g * a.S + 4 * kk + 16 * seg_beg;
+  double* my_part = s_part + ((size_t)(team * 2) * kSeg + seg) * 64 + lane * 2;   // + buf*kSeg*64
+  const double* team_part = s_part + (size_t)(team * 2) * kSeg * 64 + lane * 2;
+
+  auto row_ptr = [&](long long t) {
+    const long long row = min(a.lo + t * 8 + g, a.hi - 1);   // rows past the end re-read the last row
+    return X4 + (size_t)row * a.d4 + 4 * seg_beg + kk;
+  };
+  // tile epilogue: publish this segment's partial; the seg-0 warp of the team finishes the block
+  int buf = 0;
+  auto finish_tile = [&](long long t, double (&c)[4][2]) {
+    double* dst = my_part + buf * (kSeg * 64);
+    dst[0] = combine4(c[0][0], c[1][0], c[2][0], c[3][0]);
+    dst[1] = combine4(c[0][1], c[1][1], c[2][1], c[3][1]);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kSeg * 32) : "memory");
+    if (seg == 0) {
+      const double* src = team_part + buf * (kSeg * 64);
+      const double d0 = combine4(src[0], src[64], src[128], src[192]);
+      const double d1 = combine4(src[1], src[65], src[129], src[193]);
+      const long long i = a.lo + t * 8 + g;
+      const bool live = i < a.hi;
+      const double xxi = live ? a.xx[i] : 0.0;
+      double dm = fmin(dist_from_dot(d0, xxi, s_xxc[2 * kk]), dist_from_dot(d1, xxi, s_xxc[2 * kk + 1]));
+      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 1));
+      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 2));
+      if (live && kk == 0) {
+        const double dmin = fmin(a.m[i], dm);
         a.m[i] = dmin;
         if (a.unc) {
+          bool picked = false;
+#pragma unroll
+          for (int j = 0; j < kB; ++j) picked = picked || (s_pick[j] == i);
           double u = a.unc[i];
           if (picked) {
             u = 0.0;  // uncertainty[ind] = 0  (:848)
@@ -240,7 +328,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, int nb, double2* s_
           if (do_hist) {
             const double fb = (sc - h_lo) * h_inv;
             if (fb >= 0.0) {
-              int b = (int)fmin(fb, (double)(kNB - 1));
+              const int b = (int)fmin(fb, (double)(kNB - 1));
               atomicAdd(&s_hist[b], 1u);
               atomicAdd(&s_hist[kNB], 1u);
             }
@@ -248,42 +336,96 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, int nb, double2* s_
         }
       }
     }
+    buf ^= 1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+  };
+
+  double c[4][2];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+  if (mylen == 0) {
+    for (long long k = 0; k < nt; ++k) finish_tile(t0 + k * tstride, c);   // (tiny d: empty segment)
+  } else {
+    // flattened (tile, step) stream with an 8-deep register ring: the loads of the next tile are
+    // already in flight while the current one is finished
+    const long long F = nt * mylen;
+    long long ct = t0;                 // tile being consumed
+    int cs = 0;                        // step inside its segment
+    long long lt = t0;                 // load cursor
+    int ls = 0;
+    const float4* lp = (nt > 0) ? row_ptr(lt) : X4;
+    // a third cursor runs kPrefetch steps ahead of the loads and only touches L2
+    // (prefetch.global.L2): DRAM latency is hidden without holding registers
+    long long qt = t0;
+    int qs = 0;
+    const float4* qp = lp;
+    auto l2_prefetch = [&]() {
+      if (kPrefetch > 0 && qt < ntiles) {
+        if (kk == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(qp + 4 * qs));
+        if (++qs == mylen) {
+          qs = 0;
+          qt += tstride;
+          if (qt < ntiles) qp = row_ptr(qt);
+        }
+      }
+    };
+    for (int p = 0; p < kPrefetch; ++p) l2_prefetch();
+    float4 ring[kDepth];
+#pragma unroll
+    for (int p = 0; p < kDepth; ++p) {
+      ring[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < F) {
+        ring[p] = load_x<GUARD>(lp, 4 * ls, a.d4 - 4 * seg_beg - kk);
+        if (++ls == mylen) {
+          ls = 0;
+          lt += tstride;
+          if (lt < ntiles) lp = row_ptr(lt);
+        }
+      }
+    }
+    for (long long f0 = 0; f0 < F; f0 += kDepth) {
+#pragma unroll
+      for (int p = 0; p < kDepth; ++p) {
+        const long long f = f0 + p;
+        if (f < F) {
+          const double2 b01 = *reinterpret_cast<const double2*>(bptr + 16 * cs);
+          const double2 b23 = *reinterpret_cast<const double2*>(bptr + 16 * cs + 2);
+          const double x0 = (double)ring[p].x, x1 = (double)ring[p].y, x2 = (double)ring[p].z, x3 = (double)ring[p].w;
+          l2_prefetch();
+          if (f + kDepth < F) {          // refill the slot that was just consumed
+            ring[p] = load_x<GUARD>(lp, 4 * ls, a.d4 - 4 * seg_beg - kk);
+            if (++ls == mylen) {
+              ls = 0;
+              lt += tstride;
+              if (lt < ntiles) lp = row_ptr(lt);
+            }
+          }
+          dmma(c[0], x0, b01.x);
+          dmma(c[1], x1, b01.y);
+          dmma(c[2], x2, b23.x);
+          dmma(c[3], x3, b23.y);
+          if (++cs == mylen) {
+            finish_tile(ct, c);
+            ct += tstride;
+            cs = 0;
+          }
+        }
+      }
+    }
   }
+  __syncthreads();
   if (do_hist) {
-    __syncthreads();
     for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x)
       if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
   }
 }
 
-template <int MAXB>
-__global__ void __launch_bounds__(kPassThreads, (MAXB == 1) ? 2 : 1) pass_kernel(PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
-  if (nb <= 0) return;
-  // NBK is the power of two >= nb; the staging area is sized for MAXB by the host
-  const int nbk = nb <= 1 ? 1 : (nb <= 2 ? 2 : (nb <= 4 ? 4 : 8));
-  double2* s_c = reinterpret_cast<double2*>(smem_raw);
-  double* s_xxc = reinterpret_cast<double*>(s_c + (size_t)MAXB * a.nit * 64);
-  long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
-  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
-  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
-  if (MAXB == 1) {
-    pass_body<1>(a, 1, s_c, s_xxc, s_pick, s_hist);
-    return;
-  }
-  switch (nbk) {
-    case 1: pass_body<1>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
-    case 2: pass_body<2>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
-    case 4: pass_body<(MAXB >= 4 ? 4 : 1)>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
-    default: pass_body<(MAXB >= 8 ? 8 : 1)>(a, nb, s_c, s_xxc, s_pick, s_hist); break;
-  }
+static size_t pass_smem_bytes(int S) {
+  return (size_t)kB * S * sizeof(double) + kB * sizeof(double) + (size_t)kTeams * 2 * kSeg * 64 * sizeof(double) +
+         kB * sizeof(long long) + (kNB + 1) * sizeof(unsigned int);
 }
 
-static size_t pass_smem_bytes(int nit, int nbk) {
-  return (size_t)nbk * nit * 64 * sizeof(double2) + kB * sizeof(double) + kB * sizeof(long long) +
-         (kNB + 1) * sizeof(unsigned int);
-}
 
 // ---------------------------------------------------------------- initial scores
 __global__ void __launch_bounds__(256) score_init_kernel(long long lo, long long hi, const double* __restrict__ m,
@@ -299,7 +441,6 @@ __global__ void __launch_bounds__(256) filter_kernel(long long lo, long long hi,
                                                      const double* __restrict__ unc, const double* __restrict__ score,
                                                      unsigned int* hist, Best* partial, RankBlock* out, Ctl* ctl) {
   if (ctl->n_picked >= ctl->k) return;
-  __shared__ unsigned int s_cum[kNB];
   __shared__ double s_theta;
   __shared__ Best s_best[8];
   __shared__ unsigned int s_last;
@@ -309,30 +450,48 @@ __global__ void __launch_bounds__(256) filter_kernel(long long lo, long long hi,
   const int target = max(1, kTarget / max(1, ctl->world));
   const bool windowed = W > 0.0 && ctl->maxb > 1;
   if (windowed) {
-    // suffix sums: 256 threads x 4 bins, then a serial pass over 256 chunk totals by thread 0
+    // suffix counts cum[b] = #rows in bins >= b: 256 threads x 4 bins, warp scan + 8 warp totals
+    __shared__ unsigned int s_wtot[8];
+    __shared__ int s_bstar[8], s_bfit[8];
+    const int lane = tid & 31, wp = tid >> 5;
     unsigned int h[4], tot = 0;
 #pragma unroll
     for (int c = 3; c >= 0; --c) {
       tot += hist[tid * 4 + c];
-      h[c] = tot;
+      h[c] = tot;                    // bins c..3 of this thread's chunk
     }
-    s_cum[tid * 4 + 0] = h[0];
-    s_cum[tid * 4 + 1] = h[1];
-    s_cum[tid * 4 + 2] = h[2];
-    s_cum[tid * 4 + 3] = h[3];
+    unsigned int v = tot;            // inclusive suffix over the lanes of this warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
+      if (lane + o < 32) v += t;
+    }
+    if (lane == 0) s_wtot[wp] = v;
+    __syncthreads();
+    unsigned int run = v - tot;      // rows in bins of higher-indexed threads
+    for (int w = wp + 1; w < 8; ++w) run += s_wtot[w];
+    int bstar = -1;                  // highest bin whose suffix count reaches the target
+    int bfit = kNB;                  // lowest bin whose suffix count still fits the record capacity
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned int cum = run + h[e];
+      if (cum >= (unsigned)target) bstar = max(bstar, tid * 4 + e);
+      if (cum <= (unsigned)kCapL) bfit = min(bfit, tid * 4 + e);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      bstar = max(bstar, __shfl_xor_sync(0xffffffffu, bstar, o));
+      bfit = min(bfit, __shfl_xor_sync(0xffffffffu, bfit, o));
+    }
+    if (lane == 0) {
+      s_bstar[wp] = bstar;
+      s_bfit[wp] = bfit;
+    }
     __syncthreads();
     if (tid == 0) {
-      unsigned int run = 0;
-      int bstar = -1;    // highest bin whose suffix count reaches the target
-      int bfit = kNB;    // lowest bin whose suffix count still fits the record capacity
-      for (int c = 255; c >= 0; --c) {
-        for (int e = 3; e >= 0; --e) {
-          const unsigned int cum = run + s_cum[c * 4 + e];
-          const int b = c * 4 + e;
-          if (cum <= (unsigned)kCapL) bfit = b;
-          if (bstar < 0 && cum >= (unsigned)target) bstar = b;
-        }
-        run += s_cum[c * 4];
+      for (int w = 1; w < 8; ++w) {
+        bstar = max(bstar, s_bstar[w]);
+        bfit = min(bfit, s_bfit[w]);
       }
       if (bstar < 0) bstar = 0;
       double th;
@@ -434,7 +593,7 @@ __device__ __forceinline__ void locate(const CandView& v, int world, int pos, in
 }
 
 // ---------------------------------------------------------------- candidate x candidate distances
-__global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X, int d4, int nit,
+__global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X, int d4, int nss, int S, int guard,
                                                     const double* __restrict__ xx, const RankBlock* blocks,
                                                     const Ctl* ctl, double* __restrict__ Dcc) {
   if (ctl->n_picked >= ctl->k) return;
@@ -445,40 +604,32 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
   if (v.fallback) return;
   const int col0 = blockIdx.x * kB;
   if (col0 >= v.total) return;
-  double2* s_c = reinterpret_cast<double2*>(smem_raw);
+  double* s_c = reinterpret_cast<double*>(smem_raw);
   for (int j = 0; j < kB; ++j) {
     int r, s;
     locate(v, world, min(col0 + j, v.total - 1), r, s);
     const long long p = blocks[r].idx[s];
-    stage_center(X, d4, nit, p, j, s_c);
+    stage_center(X, d4, nss * 16, S, p, j, s_c);
     if (threadIdx.x == 0) s_xxc[j] = xx[p];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, kk = lane & 3;
   const float4* X4 = reinterpret_cast<const float4*>(X);
-  for (int g = (blockIdx.y * nwarp + warp) * kR; g < v.total; g += gridDim.y * nwarp * kR) {
-    const float4* rowp[kR];
-    long long ridx[kR];
+  for (int r0 = (blockIdx.y * nwarp + warp) * 8; r0 < v.total; r0 += gridDim.y * nwarp * 8) {
+    const int pos = min(r0 + g, v.total - 1);
+    int rr, ss;
+    locate(v, world, pos, rr, ss);
+    const long long ridx = blocks[rr].idx[ss];
+    double c[2];
+    if (guard) dmma_block<true, false>(X4 + (size_t)ridx * d4, d4, nss, s_c, S, lane, c);
+    else dmma_block<false, false>(X4 + (size_t)ridx * d4, d4, nss, s_c, S, lane, c);
+    if (r0 + g < v.total) {
+      const double xxi = xx[ridx];
+      const size_t row = (size_t)(r0 + g) * kCap;
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      rowp[r] = nullptr;
-      ridx[r] = -1;
-      if (g + r < v.total) {
-        int rr, ss;
-        locate(v, world, g + r, rr, ss);
-        ridx[r] = blocks[rr].idx[ss];
-        rowp[r] = X4 + (size_t)ridx[r] * d4;
-      }
-    }
-    double acc[kR][kB];
-    dot_tile<kB>(rowp, d4, nit, s_c, lane, acc);
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      if (lane == r && ridx[r] >= 0) {
-        const double xxi = xx[ridx[r]];
-#pragma unroll
-        for (int j = 0; j < kB; ++j)
-          if (col0 + j < v.total) Dcc[(size_t)(g + r) * kCap + col0 + j] = dist_from_dot(acc[r][j], xxi, s_xxc[j]);
+      for (int e = 0; e < 2; ++e) {
+        const int col = col0 + 2 * kk + e;
+        if (col < v.total) Dcc[row + col] = dist_from_dot(c[e], xxi, s_xxc[2 * kk + e]);
       }
     }
   }
@@ -643,57 +794,32 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
 }
 
 // distances of every row to a list of centers, for the parity tests
-__global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__ X, long long n, int d4, int nit,
-                                                       const long long* __restrict__ centers, long long mcols,
-                                                       double* __restrict__ out) {
+__global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__ X, long long n, int d4, int nss, int S,
+                                                       int guard, const double* __restrict__ xx, const long long* __restrict__ centers,
+                                                       long long mcols, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_xxc[kB];
-  double2* s_c = reinterpret_cast<double2*>(smem_raw);
+  double* s_c = reinterpret_cast<double*>(smem_raw);
   const long long col0 = (long long)blockIdx.x * kB;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, g = lane >> 2, kk = lane & 3;
   const float4* X4 = reinterpret_cast<const float4*>(X);
-  for (int j = 0; j < kB; ++j) stage_center(X, d4, nit, centers[min(col0 + j, mcols - 1)], j, s_c);
-  __syncthreads();
-  // squared norms with the canonical dot: center j against itself via the staged copy
-  if (warp == 0) {
-    for (int j = 0; j < kB; ++j) {
-      double a = 0.0;
-      for (int it = 0; it < nit; ++it) {
-        const double2 c01 = s_c[((j * nit + it) * 2) * 32 + lane], c23 = s_c[((j * nit + it) * 2 + 1) * 32 + lane];
-        a = fma(c01.x, c01.x, a);
-        a = fma(c01.y, c01.y, a);
-        a = fma(c23.x, c23.x, a);
-        a = fma(c23.y, c23.y, a);
-      }
-      a = warp_sum(a);
-      if (lane == 0) s_xxc[j] = a;
-    }
+  for (int j = 0; j < kB; ++j) {
+    const long long p = centers[min(col0 + j, mcols - 1)];
+    stage_center(X, d4, nss * 16, S, p, j, s_c);
+    if (threadIdx.x == 0) s_xxc[j] = xx[p];
   }
   __syncthreads();
-  for (long long g = ((long long)blockIdx.y * nwarp + warp) * kR; g < n; g += (long long)gridDim.y * nwarp * kR) {
-    const float4* rowp[kR];
+  for (long long r0 = ((long long)blockIdx.y * nwarp + warp) * 8; r0 < n; r0 += (long long)gridDim.y * nwarp * 8) {
+    const long long i = min(r0 + g, n - 1);
+    double c[2];
+    if (guard) dmma_block<true, false>(X4 + (size_t)i * d4, d4, nss, s_c, S, lane, c);
+    else dmma_block<false, false>(X4 + (size_t)i * d4, d4, nss, s_c, S, lane, c);
+    if (r0 + g < n) {
+      const double xxi = xx[i];
 #pragma unroll
-    for (int r = 0; r < kR; ++r) rowp[r] = (g + r < n) ? X4 + (size_t)(g + r) * d4 : nullptr;
-    double acc[kR][kB];
-    dot_tile<kB>(rowp, d4, nit, s_c, lane, acc);
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      if (g + r < n) {
-        // xx_i with the same canonical order
-        double a = 0.0;
-        for (int q = lane; q < d4; q += 32) {
-          const float4 x = __ldg(rowp[r] + q);
-          a = fma((double)x.x, (double)x.x, a);
-          a = fma((double)x.y, (double)x.y, a);
-          a = fma((double)x.z, (double)x.z, a);
-          a = fma((double)x.w, (double)x.w, a);
-        }
-        a = warp_sum(a);
-        if (lane == r) {
-#pragma unroll
-          for (int j = 0; j < kB; ++j)
-            if (col0 + j < mcols) out[(size_t)(g + r) * mcols + col0 + j] = dist_from_dot(acc[r][j], a, s_xxc[j]);
-        }
+      for (int e = 0; e < 2; ++e) {
+        const long long col = col0 + 2 * kk + e;
+        if (col < mcols) out[(size_t)i * mcols + col] = dist_from_dot(c[e], xxi, s_xxc[2 * kk + e]);
       }
     }
   }
@@ -739,7 +865,7 @@ struct Comm {
 
 // ---------------------------------------------------------------- workspace layout
 struct WsLayout {
-  size_t xx, score, hist, partial, send, recv, dcc, ctl, picks_init, total;
+  size_t xx, score, hist, partial, send, recv, dcc, ctl, total;
 };
 static WsLayout ws_layout(long long n, int world) {
   WsLayout L;
@@ -757,7 +883,6 @@ static WsLayout ws_layout(long long n, int world) {
   L.send = take(sizeof(RankBlock));
   L.recv = take(sizeof(RankBlock) * (size_t)kMaxRanks);
   L.dcc = take((size_t)kCap * kCap * 8);
-  L.picks_init = take(kB * 8);
   L.total = o;
   return L;
 }
@@ -784,44 +909,46 @@ extern "C" size_t vatlq_coreset_workspace_bytes(int64_t n, int d, int batch) {
   return ws_layout(n, kMaxRanks).total;
 }
 
+struct Geom {
+  int d4, nss, S, guard;
+  size_t smem;
+};
+static Geom geom_of(int d) {
+  Geom g;
+  g.d4 = d / 4;
+  g.nss = (d + 15) / 16;          // super-steps of 16 features (tail zero padded)
+  g.S = g.nss * 16 + 2;           // center row stride in doubles: 16 bytes mod 128
+  g.smem = (size_t)kB * g.S * sizeof(double);
+  g.guard = (d % 16) != 0;   // ragged last super-step: guarded loads
+  return g;
+}
+
 static int check_x(const float* X, int64_t n, int d, int64_t lo, int64_t hi) {
   VQ_REQUIRE(X != nullptr && ((uintptr_t)X & 15) == 0, "X must be a 16-byte aligned device pointer");
   VQ_REQUIRE(n > 0 && d > 0 && (d & 3) == 0, "d must be a positive multiple of 4");
   VQ_REQUIRE(0 <= lo && lo <= hi && hi <= n, "bad row range");
-  const int nit = (d / 4 + 31) / 32;
-  VQ_REQUIRE(pass_smem_bytes(nit, 1) <= (size_t)kMaxSmem, "d too large");
+  VQ_REQUIRE(pass_smem_bytes(geom_of(d).S) <= (size_t)kMaxSmem, "d too large (centers must fit shared memory)");
   return 0;
-}
-static int max_nbk(int nit, int batch) {
-  // two builds of the pass: GEMV form (1 center) and the batched form (staging for kB centers)
-  if (batch <= 1 || pass_smem_bytes(nit, kB) > (size_t)kMaxSmem) return 1;
-  int nbk = 1;
-  while (nbk * 2 <= kB && nbk * 2 <= batch) nbk *= 2;
-  return nbk;
 }
 
 static int launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream_t stream) {
+  const Geom g = geom_of(d);
   const int grid = sm_count() * 8;
-  row_norms_kernel<<<grid, 256, 0, stream>>>(X, n, d / 4, xx);
+  if (g.guard) row_norms_kernel<true><<<grid, 256, 0, stream>>>(X, n, g.d4, g.nss, xx);
+  else row_norms_kernel<false><<<grid, 256, 0, stream>>>(X, n, g.d4, g.nss, xx);
   VQ_LAUNCHED();
   return 0;
 }
 
-static int launch_pass(PassArgs& a, int nbk_max, cudaStream_t stream) {
+static int launch_pass(PassArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxSmem / 2)));
-    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
-  if (nbk_max == 1) {
-    // GEMV form: a small staging area, two CTAs per SM for more loads in flight
-    const size_t smem = pass_smem_bytes(a.nit, 1);
-    pass_kernel<1><<<sm_count() * (smem <= (size_t)kMaxSmem / 2 ? 2 : 1), kPassThreads, smem, stream>>>(a);
-  } else {
-    const size_t smem = pass_smem_bytes(a.nit, 8);
-    pass_kernel<8><<<sm_count(), kPassThreads, smem, stream>>>(a);
-  }
+  if ((a.d4 & 3) != 0) pass_kernel<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
+  else pass_kernel<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   VQ_LAUNCHED();
   return 0;
 }
@@ -840,14 +967,13 @@ extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_
   if (n_labeled == 0) return 0;
   VQ_REQUIRE(labeled != nullptr, "labeled is null");
   if (int e = launch_norms(X, n, d, xx, stream)) return e;
-  const int nit = (d / 4 + 31) / 32;
-  const int nbk = max_nbk(nit, kB);
-  for (int64_t c0 = 0; c0 < n_labeled; c0 += nbk) {
+  const Geom G = geom_of(d);
+  for (int64_t c0 = 0; c0 < n_labeled; c0 += kB) {
     PassArgs a{};
-    a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.unc = nullptr; a.score = nullptr; a.centers = (const long long*)labeled + c0; a.n_centers = nullptr;
-    a.n_centers_imm = (int)std::min<int64_t>(nbk, n_labeled - c0); a.ctl = nullptr; a.hist = nullptr;
-    if (int e = launch_pass(a, nbk, stream)) return e;
+    a.n_centers_imm = (int)std::min<int64_t>(kB, n_labeled - c0); a.ctl = nullptr; a.hist = nullptr;
+    if (int e = launch_pass(a, stream)) return e;
   }
   return 0;
 }
@@ -879,8 +1005,9 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   RankBlock* send = (RankBlock*)(w + L.send);
   RankBlock* recv = (world > 1) ? (RankBlock*)(w + L.recv) : send;
   double* Dcc = (double*)(w + L.dcc);
-  const int nit = (d / 4 + 31) / 32;
-  const int nbk = max_nbk(nit, std::min(batch, kB));
+  const Geom G = geom_of(d);
+  int nbk = 1;   // picks per pass: the power of two <= min(batch, kB)
+  while (nbk * 2 <= kB && nbk * 2 <= batch) nbk *= 2;
 
   Ctl h{};
   h.n_picked = 0; h.k = k; h.nb = 0; h.rule = rule; h.world = world;
@@ -901,8 +1028,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   const int own = (int)std::min<int64_t>(row_hi - row_lo, 1LL << 30);
   int fgrid = std::max(1, std::min(sm_count() * 4, (own + 255) / 256));
   VQ_REQUIRE(fgrid <= 4096, "filter grid too large");
-  const size_t pairs_smem = (size_t)kB * nit * 64 * sizeof(double2);
-  VQ_REQUIRE(pairs_smem <= (size_t)kMaxSmem, "d too large for the candidate kernel");
+  const size_t pairs_smem = G.smem;
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -916,9 +1042,9 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     VQ_CUDA(cudaMemcpyAsync(ctl, &h2, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
     VQ_CUDA(cudaMemcpyAsync(out_idx, &first_pick, 8, cudaMemcpyHostToDevice, stream));
     PassArgs a{};
-    a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl; a.hist = hist;
-    if (int e = launch_pass(a, nbk, stream)) return e;
+    if (int e = launch_pass(a, stream)) return e;
   } else {
     const long long cnt = row_hi - row_lo;
     if (cnt > 0) {
@@ -954,18 +1080,18 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       }
       if (nbk > 1) {
         dim3 pg(kCap / kB, 4);
-        pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, d / 4, nit, xx, recv, ctl, Dcc);
+        pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
         g_launches.fetch_add(1);
       }
       plan_kernel<<<1, kCap, 0, stream>>>(recv, send, Dcc, (long long*)out_idx, ctl);
       g_launches.fetch_add(1);
       PassArgs a{};
-      a.X = X; a.n = n; a.d4 = d / 4; a.nit = nit; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+      a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
       a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl;
       a.hist = (nbk > 1) ? hist : nullptr;
-      const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+        const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
       if (timed) cudaEventRecord(g_prof.ev[g_prof.used], stream);
-      rc = launch_pass(a, nbk, stream);
+      rc = launch_pass(a, stream);
       if (timed) {
         cudaEventRecord(g_prof.ev[g_prof.used + 1], stream);
         g_prof.used += 2;
@@ -1020,13 +1146,14 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
 }
 
 extern "C" int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
-                                   double* out, vatlq_stream_t stream_) {
+                                   double* out, void* ws, size_t ws_bytes, vatlq_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_x(X, n, d, 0, n)) return e;
   VQ_REQUIRE(centers && out && m > 0, "null pointer");
-  const int nit = (d / 4 + 31) / 32;
-  const size_t smem = (size_t)kB * nit * 64 * sizeof(double2);
-  VQ_REQUIRE(smem <= (size_t)kMaxSmem, "d too large");
+  VQ_REQUIRE(ws != nullptr && ws_bytes >= (size_t)n * sizeof(double), "workspace must hold n doubles");
+  const Geom G = geom_of(d);
+  double* xx = (double*)ws;
+  if (int e = launch_norms(X, n, d, xx, stream)) return e;
   static bool cfg = false;
   if (!cfg) {
     VQ_CUDA(cudaFuncSetAttribute(pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -1034,9 +1161,9 @@ extern "C" int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64
   }
   const long long colblocks = (m + kB - 1) / kB;
   VQ_REQUIRE(colblocks <= 2147483647LL, "too many centers");
-  const int gy = (int)std::max<long long>(1, std::min<long long>(64, (n + 31) / 32));
+  const int gy = (int)std::max<long long>(1, std::min<long long>(64, (n + 127) / 128));
   dim3 grid((unsigned)colblocks, (unsigned)gy);
-  pairwise_kernel<<<grid, 256, smem, stream>>>(X, n, d / 4, nit, (const long long*)centers, m, out);
+  pairwise_kernel<<<grid, 256, G.smem, stream>>>(X, n, G.d4, G.nss, G.S, G.guard, xx, (const long long*)centers, m, out);
   VQ_LAUNCHED();
   return 0;
 }

@@ -167,21 +167,19 @@ scan_runs_64x48(const float* __restrict__ H, const uint8_t* __restrict__ is_prev
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float m4 = fmaxf(fmaxf(v[r].x, v[r].y), fmaxf(v[r].z, v[r].w));
-      if (m4 >= thr) {
+      if (m4 >= thr || m4 == gmax) {  // (a negative maximum is below its own half: thr > gmax)
         const int q = tid + r * kScanThreads;
         const int y = q / (FW / 4), x0 = (q % (FW / 4)) * 4;
         const float e[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (e[c] >= thr) {
-            if (is_local_max<FH, FW>(s_map, y, x0 + c, e[c], FH, FW)) {
-              ps += e[c];
-              pc += 1;
-            }
-            if (e[c] == gmax && cand == 0x7fffffff) {
-              cand = q * 4 + c;
-              quarter_shift(s_map, y, x0 + c, FH, FW, gmax, cx, cy);
-            }
+          if (e[c] >= thr && is_local_max<FH, FW>(s_map, y, x0 + c, e[c], FH, FW)) {
+            ps += e[c];
+            pc += 1;
+          }
+          if (e[c] == gmax && cand == 0x7fffffff) {
+            cand = q * 4 + c;
+            quarter_shift(s_map, y, x0 + c, FH, FW, gmax, cx, cy);
           }
         }
       }
@@ -299,9 +297,9 @@ scan_generic(const float* __restrict__ H, const uint8_t* __restrict__ is_prev,
   int pc = 0, cand = 0x7fffffff;
   for (int p = tid; p < npx; p += kScanThreads) {
     const float val = s_map[p];
-    if (val >= thr) {
+    if (val >= thr || val == gmax) {
       const int y = p / w, x = p % w;
-      if (is_local_max<0, 0>(s_map, y, x, val, h, w)) {
+      if (val >= thr && is_local_max<0, 0>(s_map, y, x, val, h, w)) {
         ps += val;
         pc += 1;
       }

@@ -251,7 +251,8 @@ def pairwise_dist(X: torch.Tensor, centers) -> torch.Tensor:
     n, d = X.shape
     c = torch.as_tensor(np.asarray(centers, dtype=np.int64)).to(X.device)
     out = torch.empty((n, c.numel()), dtype=torch.float64, device=X.device)
+    ws = torch.empty(n, dtype=torch.float64, device=X.device)
     with torch.cuda.device(X.device):
-        _lib.check(_lib.lib().vatlq_pairwise_dist(_ptr(X), n, d, _ptr(c), c.numel(), _ptr(out), _stream()),
+        _lib.check(_lib.lib().vatlq_pairwise_dist(_ptr(X), n, d, _ptr(c), c.numel(), _ptr(out), _ptr(ws), n * 8, _stream()),
                    "vatlq_pairwise_dist")
     return out

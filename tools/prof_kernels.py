@@ -1,5 +1,5 @@
 """Short driver for ncu captures: one heat-map scan and a few core-set passes at bench scale.
-    ncu --set full --clock-control none --import-source on -k regex:'scan_runs|pass_kernel' -o gpurun_out/prof python tools/prof_kernels.py
+    ncu --set full --clock-control none --import-source on -k regex:'scan_tma|pass_kernel' -o gpurun_out/prof python tools/prof_kernels.py
 """
 import os
 import sys

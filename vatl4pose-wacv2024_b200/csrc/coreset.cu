@@ -102,15 +102,15 @@ __device__ __forceinline__ double dist_from_dot(double dot, double xxi, double x
 // is k-slot kk of MMA e, i.e. feature 16s+4kk+e.  The B operand of lane (g, kk) is center g
 // at the same feature.  Output: lane holds (row g, centers 2kk and 2kk+1).
 //
-// CANONICAL DOT: the feature axis is cut into kSeg = 4 segments of ceil(nss/4) super-steps.
+// CANONICAL DOT: the feature axis is cut into kSeg = 8 segments of ceil(nss/8) super-steps.
 // Inside a segment, element e (0..3) of every float4 feeds its own sequential DMMA chain
-// (four independent chains hide the ~130-cycle dependent-issue latency of DMMA), and
-//   P_seg = (c_0 + c_1) + (c_2 + c_3),     dot = (P0 + P1) + (P2 + P3).
+// (four independent chains hide the dependent-issue latency of DMMA), and
+//   P_seg = (c_0 + c_1) + (c_2 + c_3),   dot = ((P0 + P1) + (P2 + P3)) + ((P4 + P5) + (P6 + P7)).
 // Every kernel (norms, pass, candidate pairs, pairwise) evaluates exactly this, so d(i,c) has
-// the same bits wherever it is computed and dot(x,x) == xx (d(c,c) == 0).  In the pass the four
-// segments of a block are computed by the four warps of a "team" in parallel (split-K), which
-// keeps all 16 warps of an SM busy even when a rank owns only ~20 k rows.
-constexpr int kSeg = 4;
+// the same bits wherever it is computed and dot(x,x) == xx (d(c,c) == 0).  In the pass the eight
+// segments of a block are computed by eight warps in parallel (split-K): a warp then only ever
+// needs 1/8 of every centre, which fits its REGISTERS (see pass_kernel_reg).
+constexpr int kSeg = 8;
 #ifndef VQ_DEPTH
 #define VQ_DEPTH 8
 #endif
@@ -167,6 +167,10 @@ __device__ __forceinline__ void dmma_step_self(double (&c)[4][2], const float4& 
 __device__ __forceinline__ double combine4(double p0, double p1, double p2, double p3) {
   return __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
 }
+__device__ __forceinline__ double combine8(const double* p, int stride) {
+  return __dadd_rn(combine4(p[0], p[stride], p[2 * stride], p[3 * stride]),
+                   combine4(p[4 * stride], p[5 * stride], p[6 * stride], p[7 * stride]));
+}
 
 // canonical dots of one 8-row block (this lane's row pointer `rowp`, never null) against the 8
 // staged centers, all four segments by one warp (four independent chains): used by the small
@@ -177,34 +181,38 @@ __device__ __forceinline__ void dmma_block(const float4* rowp, int d4, int nss, 
   const int g = lane >> 2, kk = lane & 3;
   const int seglen = (nss + kSeg - 1) / kSeg;
   const double* bptr = SELF ? nullptr : s_c + (size_t)g * S + 4 * kk;
-  double c[kSeg][4][2];
+  double P[2][kSeg];
+  // the segments are independent chains: run them four at a time (register budget)
 #pragma unroll
-  for (int q = 0; q < kSeg; ++q)
+  for (int grp = 0; grp < kSeg / 4; ++grp) {
+    double c[4][4][2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) c[q][e][0] = c[q][e][1] = 0.0;
-  for (int s = 0; s < seglen; ++s) {
-    float4 x[kSeg];
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int q = 0; q < kSeg; ++q) {
-      const int ss = q * seglen + s;
-      x[q] = (ss < nss) ? load_x<GUARD>(rowp, 4 * ss + kk, d4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+      for (int e = 0; e < 4; ++e) c[q][e][0] = c[q][e][1] = 0.0;
+    for (int s = 0; s < seglen; ++s) {
+      float4 x[4];
 #pragma unroll
-    for (int q = 0; q < kSeg; ++q) {
-      const int ss = q * seglen + s;
-      if (ss < nss) {
-        if (SELF) dmma_step_self(c[q], x[q]);
-        else dmma_step(c[q], x[q], bptr + 16 * ss);
+      for (int q = 0; q < 4; ++q) {
+        const int ss = (grp * 4 + q) * seglen + s;
+        x[q] = (ss < nss) ? load_x<GUARD>(rowp, 4 * ss + kk, d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ss = (grp * 4 + q) * seglen + s;
+        if (ss < nss) {
+          if (SELF) dmma_step_self(c[q], x[q]);
+          else dmma_step(c[q], x[q], bptr + 16 * ss);
+        }
       }
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) P[h][grp * 4 + q] = combine4(c[q][0][h], c[q][1][h], c[q][2][h], c[q][3][h]);
   }
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    double p[kSeg];
-#pragma unroll
-    for (int q = 0; q < kSeg; ++q) p[q] = combine4(c[q][0][h], c[q][1][h], c[q][2][h], c[q][3][h]);
-    out[h] = combine4(p[0], p[1], p[2], p[3]);
-  }
+  for (int h = 0; h < 2; ++h) out[h] = combine8(P[h], 1);
 }
 
 // ---------------------------------------------------------------- squared row norms
@@ -241,10 +249,10 @@ struct PassArgs {
   unsigned int* hist;        // null: no histogram
 };
 
-constexpr int kTeams = kPassThreads / 32 / kSeg;   // 4 teams of 4 warps
+constexpr int kTeams = kPassThreads / 32 / kSeg;   // 2 teams of 8 warps
 
 template <bool GUARD>
-__global__ void __launch_bounds__(kPassThreads, 1) pass_kernel(PassArgs a) {
+__global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
   if (nb <= 0) return;
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel(PassArgs a) {
   long long* s_pick = reinterpret_cast<long long*>(s_part + kTeams * 2 * kSeg * 64);
   unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
-  const int team = warp >> 2, seg = warp & 3;
+  const int team = warp / kSeg, seg = warp % kSeg;
   const int dpad = a.nss * 16;
   if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
   for (int j = 0; j < kB; ++j) {
@@ -303,8 +311,8 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel(PassArgs a) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kSeg * 32) : "memory");
     if (seg == 0) {
       const double* src = team_part + buf * (kSeg * 64);
-      const double d0 = combine4(src[0], src[64], src[128], src[192]);
-      const double d1 = combine4(src[1], src[65], src[129], src[193]);
+      const double d0 = combine8(src, 64);
+      const double d1 = combine8(src + 1, 64);
       const long long i = a.lo + t * 8 + g;
       const bool live = i < a.hi;
       const double xxi = live ? a.xx[i] : 0.0;
@@ -413,6 +421,146 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel(PassArgs a) {
         }
       }
     }
+  }
+  __syncthreads();
+  if (do_hist) {
+    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x)
+      if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
+  }
+}
+
+// ---------------------------------------------------------------- the pass over X, fast path
+// d == 8 * 16 * STEPS (2048 for STEPS = 16).  One CTA = 8 warps = the 8 K-segments of one 8-row
+// tile at a time.  Warp w keeps ITS 1/8 of the 8 centres in registers as fp64 B operands
+// (STEPS x 4 doubles per lane), so the inner loop has no shared-memory traffic at all: per
+// super-step one 16-byte global load (a STEPS-deep register ring keeps a whole tile in flight
+// per lane), four fp32->fp64 converts and four DMMAs.  The per-tile split-K reduction goes
+// through 4 KB of shared memory: every warp then finishes one row of the tile (lane j <- centre j).
+template <int STEPS>
+__global__ void __launch_bounds__(kSeg * 32, 1) pass_kernel_reg(PassArgs a) {
+  __shared__ double s_part[2][kSeg][64];   // [buf][segment][row*8 + centre]
+  __shared__ double s_xxc[kB];
+  __shared__ long long s_pick[kB];
+  __shared__ unsigned int s_hist[kNB + 1];
+  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  if (nb <= 0) return;
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
+  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  const float4* X4 = reinterpret_cast<const float4*>(a.X);
+  const int lane_off = seg * (STEPS * 4) + kk;      // float4 offset of this lane inside a row
+
+  // B operands: centre g (padded with the last centre: min() is idempotent), this warp's segment
+  double breg[STEPS][4];
+  {
+    const long long pg = a.centers[min(g, nb - 1)];
+    const float4* cp = X4 + (size_t)pg * a.d4 + lane_off;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 v = __ldg(cp + 4 * s);
+      breg[s][0] = (double)v.x;
+      breg[s][1] = (double)v.y;
+      breg[s][2] = (double)v.z;
+      breg[s][3] = (double)v.w;
+    }
+  }
+  if (threadIdx.x < kB) {
+    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];
+    s_xxc[threadIdx.x] = a.xx[p];
+    s_pick[threadIdx.x] = p;
+  }
+  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
+  int rule = 0;
+  if (a.ctl) {
+    rule = a.ctl->rule;
+    wd = a.ctl->wd;
+    wu = a.ctl->wu;
+    if (do_hist) {
+      h_lo = a.ctl->U - a.ctl->W;
+      h_inv = (double)kNB / a.ctl->W;
+      for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
+    }
+  }
+  __syncthreads();
+
+  const long long ntiles = (a.hi - a.lo + 7) / 8;
+  auto row_ptr = [&](long long t) {
+    const long long row = min(a.lo + t * 8 + g, a.hi - 1);   // rows past the end re-read the last row
+    return X4 + (size_t)row * a.d4 + lane_off;
+  };
+  long long t = blockIdx.x;
+  float4 ring[STEPS];
+  if (t < ntiles) {
+    const float4* p0 = row_ptr(t);
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(p0 + 4 * s);
+  }
+  int buf = 0;
+  for (; t < ntiles; t += gridDim.x) {
+    const long long tn = t + gridDim.x;
+    const bool has_next = tn < ntiles;
+    const float4* np = row_ptr(has_next ? tn : t);
+    // this warp finishes row `seg` of the tile: fetch its state early (latency hidden by the MMAs)
+    const long long i = a.lo + t * 8 + seg;
+    const bool live = i < a.hi;
+    double xxi = 0.0, mi = 0.0, ui = 0.0;
+    if (live && lane == 0) {
+      xxi = a.xx[i];
+      mi = a.m[i];
+      if (a.unc) ui = a.unc[i];
+    }
+    double c[4][2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 x = ring[s];
+      if (has_next) ring[s] = ldg_stream(np + 4 * s);
+      dmma(c[0], (double)x.x, breg[s][0]);
+      dmma(c[1], (double)x.y, breg[s][1]);
+      dmma(c[2], (double)x.z, breg[s][2]);
+      dmma(c[3], (double)x.w, breg[s][3]);
+    }
+    // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
+    *reinterpret_cast<double2*>(&s_part[buf][seg][lane * 2]) =
+        make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
+    __syncthreads();
+    if (live) {   // warp-uniform
+      xxi = __shfl_sync(0xffffffffu, xxi, 0);
+      double dm = INFINITY;
+      bool mine = false;
+      if (lane < kB) {
+        const double dot = combine8(&s_part[buf][0][seg * 8 + lane], 64);
+        dm = dist_from_dot(dot, xxi, s_xxc[lane]);
+        mine = s_pick[lane] == i;
+      }
+      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 1));
+      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 2));
+      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 4));
+      const bool picked = __any_sync(0xffffffffu, mine);
+      if (lane == 0) {
+        const double dmin = fmin(mi, dm);
+        a.m[i] = dmin;
+        if (a.unc) {
+          double u = ui;
+          if (picked) {
+            u = 0.0;  // uncertainty[ind] = 0  (:848)
+            a.unc[i] = 0.0;
+          }
+          const double sc = score_of(rule, wd, wu, dmin, u);
+          a.score[i] = sc;
+          if (do_hist) {
+            const double fb = (sc - h_lo) * h_inv;
+            if (fb >= 0.0) {
+              const int b = (int)fmin(fb, (double)(kNB - 1));
+              atomicAdd(&s_hist[b], 1u);
+              atomicAdd(&s_hist[kNB], 1u);
+            }
+          }
+        }
+      }
+    }
+    buf ^= 1;
   }
   __syncthreads();
   if (do_hist) {
@@ -943,12 +1091,13 @@ static int launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream
 static int launch_pass(PassArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    VQ_CUDA(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
-  if ((a.d4 & 3) != 0) pass_kernel<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
-  else pass_kernel<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
+  if (a.d4 == kSeg * 4 * 16) pass_kernel_reg<16><<<sm_count(), kSeg * 32, 0, stream>>>(a);          // d = 2048
+  else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
+  else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   VQ_LAUNCHED();
   return 0;
 }

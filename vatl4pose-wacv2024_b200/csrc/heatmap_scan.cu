@@ -2,11 +2,11 @@
 // streaming pass over the (n,J,h,w) fp32 pool.  See include/vatlq.h for the reference
 // functions this replaces and DESIGN.md §scan for the data flow.
 //
-// Work decomposition: CTA (run r, joint j) walks frames [a,b) of joint j.  A thread owns the
-// same 12 pixels (3 float4) of every frame, so frame t-1 stays in registers for the
-// |H_t - H_{t-1}| term and every byte of H is fetched from HBM exactly once (plus one halo
-// frame per run).  The map is also parked in shared memory, but only the few pixels that
-// reach half of the map maximum ever look at their 3x3 neighbourhood there:
+// Work decomposition (fast path): one warp walks a run of consecutive frames of one joint.
+// Maps land in shared memory by 1-D TMA bulk copies and are pulled into registers, where frame
+// t-1 stays for the |H_t - H_{t-1}| term, so every byte of H is fetched from HBM exactly once
+// (plus one halo map per run).  Only the few pixels that reach half of the map maximum ever
+// look at their 3x3 neighbourhood in shared memory:
 //   * the largest peak of a map is its global maximum whenever that maximum is > 0, and
 //     when it is <= 0 the 0.5*max threshold rejects everything but exact zeros
 //     (local_peak.py:5-10), so "kept peak" == "pixel >= 0.5*gmax that is a 3x3 (zero-padded)
@@ -74,174 +74,180 @@ __device__ __forceinline__ void quarter_shift(const float* __restrict__ s_map, i
   }
 }
 
+constexpr int FH = 64, FW = 48, FPIX = FH * FW, FQ = FPIX / 4;  // 3072 px, 768 float4 per map
+
 // ------------------------------------------------------------------------------------
-// fast path: 64x48 maps (every config of the reference), 256 threads, 3 float4 per thread
+// fast path, 64x48 maps (every config of the reference): one WARP owns a run of consecutive frames of one joint.
+// Lane 0 keeps kStages-1 maps in flight with cp.async.bulk (1-D TMA bulk copy, 12 288 B each,
+// completion counted on an mbarrier per stage); the warp pulls the landed map into registers
+// (24 float4 per lane), where it stays to serve as frame t-1 of the next step, so every byte
+// of H crosses HBM once and shared memory is only a landing zone + the 3x3 neighbourhood
+// lookups of the few pixels above half of the map maximum.  No __syncthreads anywhere: all
+// reductions are warp shuffles, warps of a CTA only share the launch.
 // ------------------------------------------------------------------------------------
-constexpr int FH = 64, FW = 48, FPIX = FH * FW, FQ = FPIX / 4;  // 3072 px, 768 float4
+#ifndef VQ_SCAN_WARPS
+#define VQ_SCAN_WARPS 8
+#endif
+#ifndef VQ_SCAN_STAGES
+#define VQ_SCAN_STAGES 2
+#endif
+constexpr int kTmaWarps = VQ_SCAN_WARPS;
+constexpr int kStages = VQ_SCAN_STAGES;
+constexpr int kMapBytes = FPIX * 4;              // 12 288
+constexpr int kLaneQ = FQ / 32;                  // 24 float4 per lane
+constexpr size_t kTmaSmem = (size_t)kTmaWarps * kStages * kMapBytes + (size_t)kTmaWarps * kStages * 8;
 
-__global__ void __launch_bounds__(kScanThreads, 4)
-scan_runs_64x48(const float* __restrict__ H, const uint8_t* __restrict__ is_prev,
-                const uint8_t* __restrict__ is_next, int64_t n, int J,
-                const float* __restrict__ halo_prev, const float* __restrict__ halo_next,
-                int run_len, ScanOut out) {
-  __shared__ __align__(16) float s_map[FPIX];
-  __shared__ float s_wmax[kWarps];
-  __shared__ float s_wsum[kWarps];
-  __shared__ float s_wps[kWarps];
-  __shared__ int s_wpc[kWarps];
-  __shared__ int s_arg[2];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = blockIdx.y;
-  const int64_t a = (int64_t)blockIdx.x * run_len;
-  const int64_t b = min(n, a + (int64_t)run_len);
-  if (a >= b) return;
-  const bool has_hp = halo_prev != nullptr, has_hn = halo_next != nullptr;
-  const size_t frame_q = (size_t)J * FQ;  // float4 per frame
-  const float4* base = reinterpret_cast<const float4*>(H) + (size_t)j * FQ;
-
-  if (tid < 2) s_arg[tid] = 0x7fffffff;
-
-  float4 v[3], pv[3], nx[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) v[r] = ldg_stream(base + (size_t)a * frame_q + tid + r * kScanThreads);
-  if (pair_wanted(a, n, is_prev, is_next, has_hp, has_hn)) {
-    const float4* p = (a > 0) ? base + (size_t)(a - 1) * frame_q
-                              : reinterpret_cast<const float4*>(halo_prev) + (size_t)j * FQ;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) pv[r] = ldg_stream(p + tid + r * kScanThreads);
-  } else {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) pv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
   }
-  __syncthreads();
+}
 
-  for (int64_t t = a; t < b; ++t) {
-    const int buf = (int)(t & 1);
-    if (t + 1 < b) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) nx[r] = ldg_stream(base + (size_t)(t + 1) * frame_q + tid + r * kScanThreads);
+__global__ void __launch_bounds__(kTmaWarps * 32, 1)
+scan_tma_64x48(const float* __restrict__ H, const uint8_t* __restrict__ is_prev,
+               const uint8_t* __restrict__ is_next, int64_t n, int J,
+               const float* __restrict__ halo_prev, const float* __restrict__ halo_next,
+               int run_len, int64_t n_runs, ScanOut out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t task = (int64_t)blockIdx.x * kTmaWarps + warp;   // task = run * J + joint
+  if (task >= n_runs * J) return;
+  const int j = (int)(task % J);
+  const int64_t a = (task / J) * run_len;
+  const int64_t b = min(n, a + (int64_t)run_len);
+  float* stage0 = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * FPIX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTmaWarps * kStages * kMapBytes) + warp * kStages;
+  const bool has_hp = halo_prev != nullptr, has_hn = halo_next != nullptr;
+
+  // frames this warp streams: [first, last]; first == a-1 only feeds the |H_a - H_{a-1}| term,
+  // last == n (the halo that follows the pool) only closes the final pair
+  const int64_t first = pair_wanted(a, n, is_prev, is_next, has_hp, has_hn) ? a - 1 : a;
+  const bool tail_pair = (b == n) && pair_wanted(n, n, is_prev, is_next, has_hp, has_hn);
+  const int64_t last = tail_pair ? n : b - 1;
+  const int64_t count = last - first + 1;
+  auto src_of = [&](int64_t f) -> const float* {
+    if (f < 0) return halo_prev + (size_t)j * FPIX;
+    if (f >= n) return halo_next + (size_t)j * FPIX;
+    return H + ((size_t)f * J + j) * FPIX;
+  };
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < kStages && s < count; ++s) {
+      mbar_expect_tx(&bars[s], kMapBytes);
+      tma_load_1d(stage0 + (size_t)s * FPIX, src_of(first + s), kMapBytes, &bars[s]);
     }
-    const bool want = pair_wanted(t, n, is_prev, is_next, has_hp, has_hn);
+  }
+  __syncwarp();
 
-    // ---- pass 1: map maximum, |H_t - H_{t-1}|, park the map in shared memory
-    float lmax = fmaxf(fmaxf(fmaxf(v[0].x, v[0].y), fmaxf(v[0].z, v[0].w)),
-                       fmaxf(fmaxf(fmaxf(v[1].x, v[1].y), fmaxf(v[1].z, v[1].w)),
-                             fmaxf(fmaxf(v[2].x, v[2].y), fmaxf(v[2].z, v[2].w))));
-    float s = 0.0f;
-    if (want) {
+  float4 pv[kLaneQ];   // frame f-1 (registers)
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        s += fabsf(v[r].x - pv[r].x);
-        s += fabsf(v[r].y - pv[r].y);
-        s += fabsf(v[r].z - pv[r].z);
-        s += fabsf(v[r].w - pv[r].w);
+  for (int r = 0; r < kLaneQ; ++r) pv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t i = 0; i < count; ++i) {
+    const int64_t f = first + i;
+    const int s = (int)(i % kStages);
+    const float* cur = stage0 + (size_t)s * FPIX;
+    mbar_wait(&bars[s], (uint32_t)((i / kStages) & 1));
+    const float4* cur4 = reinterpret_cast<const float4*>(cur);
+    const bool want = (f >= a) && pair_wanted(f, n, is_prev, is_next, has_hp, has_hn);
+
+    // ---- pass 1: pull the map into registers; map maximum and |H_f - H_{f-1}|
+    // (four independent chains each: a lone warp per scheduler has no other latency hiding)
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kLaneQ; ++r) {
+      const float4 c = cur4[r * 32 + lane];
+      if (want) {
+        sm.x += fabsf(c.x - pv[r].x);
+        sm.y += fabsf(c.y - pv[r].y);
+        sm.z += fabsf(c.z - pv[r].z);
+        sm.w += fabsf(c.w - pv[r].w);
       }
+      mx.x = fmaxf(mx.x, c.x);
+      mx.y = fmaxf(mx.y, c.y);
+      mx.z = fmaxf(mx.z, c.z);
+      mx.w = fmaxf(mx.w, c.w);
+      pv[r] = c;
     }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) reinterpret_cast<float4*>(s_map)[tid + r * kScanThreads] = v[r];
-    lmax = warp_max(lmax);
-    s = warp_sum(s);
-    if (lane == 0) {
-      s_wmax[warp] = lmax;
-      s_wsum[warp] = s;
+    float sum = (sm.x + sm.y) + (sm.z + sm.w);
+    const float lmax = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
+    if (f >= a) {
+      sum = warp_sum(sum);
+      if (lane == 0) out.pair_sum[(size_t)f * J + j] = want ? (double)sum : 0.0;
     }
-    __syncthreads();  // (1) map + warp partials visible
-    float gmax = s_wmax[0];
+    if (f >= a && f < n) {
+      const float gmax = warp_max(lmax);
+      // ---- pass 2: only pixels >= 0.5*gmax can be kept peaks; only pixels == gmax the argmax
+      const float thr = 0.5f * gmax;
+      float ps = 0.0f, cx = 0.f, cy = 0.f;
+      int pc = 0, cand = 0x7fffffff;
+      unsigned hot = 0;   // which of this lane's float4 hold a pixel >= thr (or the maximum)
 #pragma unroll
-    for (int k = 1; k < kWarps; ++k) gmax = fmaxf(gmax, s_wmax[k]);
-    if (tid == 0) {
-      double ps = 0.0;
-#pragma unroll
-      for (int k = 0; k < kWarps; ++k) ps += (double)s_wsum[k];
-      out.pair_sum[(size_t)t * J + j] = want ? ps : 0.0;
-      s_arg[buf ^ 1] = 0x7fffffff;  // all readers of the previous frame's slot are past (1)
-    }
-
-    // ---- pass 2: only pixels >= 0.5*gmax can be kept peaks; only pixels == gmax the argmax
-    const float thr = 0.5f * gmax;
-    float ps = 0.0f;
-    int pc = 0;
-    int cand = 0x7fffffff;
-    float cx = 0.f, cy = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float m4 = fmaxf(fmaxf(v[r].x, v[r].y), fmaxf(v[r].z, v[r].w));
-      if (m4 >= thr || m4 == gmax) {  // (a negative maximum is below its own half: thr > gmax)
-        const int q = tid + r * kScanThreads;
+      for (int r = 0; r < kLaneQ; ++r) {
+        const float m4 = fmaxf(fmaxf(pv[r].x, pv[r].y), fmaxf(pv[r].z, pv[r].w));
+        if (m4 >= thr || m4 == gmax) hot |= 1u << r;  // (a negative maximum is below its own half: thr > gmax)
+      }
+      while (hot) {        // rolled on purpose: a handful of float4 per map, small code
+        const int r = __ffs(hot) - 1;
+        hot &= hot - 1;
+        const int q = r * 32 + lane;
         const int y = q / (FW / 4), x0 = (q % (FW / 4)) * 4;
-        const float e[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        const float4 c4 = cur4[q];
+        const float e[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (e[c] >= thr && is_local_max<FH, FW>(s_map, y, x0 + c, e[c], FH, FW)) {
+          if (e[c] >= thr && is_local_max<FH, FW>(cur, y, x0 + c, e[c], FH, FW)) {
             ps += e[c];
             pc += 1;
           }
           if (e[c] == gmax && cand == 0x7fffffff) {
             cand = q * 4 + c;
-            quarter_shift(s_map, y, x0 + c, FH, FW, gmax, cx, cy);
+            quarter_shift(cur, y, x0 + c, FH, FW, gmax, cx, cy);
           }
         }
       }
-    }
-    if (cand != 0x7fffffff) atomicMin(&s_arg[buf], cand);
-    if (__any_sync(0xffffffffu, pc > 0)) {
+      const int best = __reduce_min_sync(0xffffffffu, cand);   // first flat argmax (np.argmax)
       ps = warp_sum(ps);
       pc = warp_sum(pc);
-    }
-    if (lane == 0) {
-      s_wps[warp] = ps;
-      s_wpc[warp] = pc;
-    }
-    __syncthreads();  // (2) all reads of s_map done; partials + argmax visible
-    const size_t o = (size_t)t * J + j;
-    if (tid == 0) {
-      float tps = 0.0f;
-      int tpc = 0;
-#pragma unroll
-      for (int k = 0; k < kWarps; ++k) {
-        tps += s_wps[k];
-        tpc += s_wpc[k];
+      const size_t o = (size_t)f * J + j;
+      if (lane == 0) {
+        out.psum[o] = ps;
+        out.pcnt[o] = pc;
+        out.maxv[o] = gmax;
       }
-      out.psum[o] = tps;
-      out.pcnt[o] = tpc;
-      out.maxv[o] = gmax;
+      if (cand == best) {
+        out.hmxy[o * 2 + 0] = cx;
+        out.hmxy[o * 2 + 1] = cy;
+      }
     }
-    if (cand != 0x7fffffff && cand == s_arg[buf]) {
-      out.hmxy[o * 2 + 0] = cx;
-      out.hmxy[o * 2 + 1] = cy;
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      pv[r] = v[r];
-      v[r] = nx[r];
+    // ---- the stage is free: refill it with frame f + kStages
+    __syncwarp();
+    if (lane == 0 && i + kStages < count) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[s], kMapBytes);
+      tma_load_1d(stage0 + (size_t)s * FPIX, src_of(f + kStages), kMapBytes, &bars[s]);
     }
   }
-
-  // trailing pair (frame n-1 with the halo frame that follows the pool): last run only
-  if (b == n && pair_wanted(n, n, is_prev, is_next, has_hp, has_hn)) {
-    const float4* p = reinterpret_cast<const float4*>(halo_next) + (size_t)j * FQ;
-    float s = 0.0f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float4 h4 = ldg_stream(p + tid + r * kScanThreads);
-      s += fabsf(h4.x - pv[r].x);
-      s += fabsf(h4.y - pv[r].y);
-      s += fabsf(h4.z - pv[r].z);
-      s += fabsf(h4.w - pv[r].w);
-    }
-    s = warp_sum(s);
-    if (lane == 0) s_wsum[warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-      double ps = 0.0;
-#pragma unroll
-      for (int k = 0; k < kWarps; ++k) ps += (double)s_wsum[k];
-      out.pair_sum[(size_t)n * J + j] = ps;
-    }
-  } else if (b == n && tid == 0) {
-    out.pair_sum[(size_t)n * J + j] = 0.0;
-  }
+  if (b == n && !tail_pair && lane == 0) out.pair_sum[(size_t)n * J + j] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------
@@ -501,18 +507,24 @@ extern "C" int vatlq_heatmap_scan(const float* H, const uint8_t* is_prev, const 
   const bool fast = (h == FH && w == FW) && (halo_prev == nullptr || ((uintptr_t)halo_prev & 15) == 0) &&
                     (halo_next == nullptr || ((uintptr_t)halo_next & 15) == 0);
   if (fast) {
-    // enough CTAs for ~2 waves of 4 resident CTAs per SM, runs no shorter than 8 frames so the
-    // halo re-read stays <= 1/8 of the traffic on tiny pools
-    const int64_t target = (int64_t)sm_count() * 4 * 2;
-    int64_t runs = (target + J - 1) / J;
+    // one warp per (run, joint) task, ~4 tasks per warp slot so that CTAs finishing early are
+    // replaced; runs no shorter than 8 frames keep the halo re-read <= 1/8 of the traffic.
+    // 8 warps x 2 stages per SM measured best (6.8 TB/s; 6x3 5.3, 4x4 3.7: tools/tune_scan.py)
+    const int64_t slots = (int64_t)sm_count() * kTmaWarps;
+    int64_t runs = (slots * 4 + J - 1) / J;
     int64_t run_len = (n + runs - 1) / runs;
     if (run_len < 8) run_len = 8;
     if (run_len > n) run_len = n;
     runs = (n + run_len - 1) / run_len;
-    VQ_REQUIRE(J <= 65535, "J too large");
-    dim3 grid((unsigned)runs, (unsigned)J);
-    scan_runs_64x48<<<grid, kScanThreads, 0, stream>>>(H, is_prev, is_next, n, J, halo_prev, halo_next,
-                                                       (int)run_len, so);
+    const int64_t tasks = runs * J;
+    static bool cfg = false;
+    if (!cfg) {
+      VQ_CUDA(cudaFuncSetAttribute(scan_tma_64x48, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+      cfg = true;
+    }
+    VQ_REQUIRE((tasks + kTmaWarps - 1) / kTmaWarps <= 2147483647LL, "grid too large");
+    scan_tma_64x48<<<(unsigned)((tasks + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, kTmaSmem, stream>>>(
+        H, is_prev, is_next, n, J, halo_prev, halo_next, (int)run_len, runs, so);
     VQ_LAUNCHED();
   } else {
     const size_t smem = (size_t)h * w * sizeof(float);

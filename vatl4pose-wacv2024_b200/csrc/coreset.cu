@@ -430,119 +430,159 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
 }
 
 // ---------------------------------------------------------------- the pass over X, fast path
-// d == 8 * 16 * STEPS (2048 for STEPS = 16).  One CTA = 8 warps = the 8 K-segments of one 8-row
-// tile at a time.  Warp w keeps ITS 1/8 of the 8 centres in registers as fp64 B operands
-// (STEPS x 4 doubles per lane), so the inner loop has no shared-memory traffic at all: per
-// super-step one 16-byte global load (a STEPS-deep register ring keeps a whole tile in flight
-// per lane), four fp32->fp64 converts and four DMMAs.  The per-tile split-K reduction goes
-// through 4 KB of shared memory: every warp then finishes one row of the tile (lane j <- centre j).
+// d == 8 * 16 * STEPS (2048 for STEPS = 16).  Warp-specialised, one CTA per SM:
+//   * 8 COMPUTE warps = the 8 K-segments of one 8-row tile at a time.  Warp w keeps ITS 1/8 of
+//     the 8 centres in registers as fp64 B operands (STEPS x 4 doubles per lane), so the inner
+//     loop has no shared-memory traffic: per super-step one 16-byte global load (a STEPS-deep
+//     register ring keeps a whole tile per lane in flight), four fp32->fp64 converts, four
+//     DMMAs.  A tile ends with one 16-byte shared store of the segment's partial dots and a
+//     non-blocking bar.arrive — compute warps never wait for anything but their own loads.
+//   * 4 EPILOGUE warps consume the partials through a 4-deep ring of named barriers: split-K
+//     reduction in the canonical order, distance, running minimum, unc/score update, histogram.
+// setmaxnreg moves registers from the epilogue warpgroup (40) to the compute warpgroups (232).
+constexpr int kPartBufs = 4;
+constexpr int kWsThreads = (kSeg + 4) * 32;   // 8 compute + 4 epilogue warps
+
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <int STEPS>
-__global__ void __launch_bounds__(kSeg * 32, 1) pass_kernel_reg(PassArgs a) {
-  __shared__ double s_part[2][kSeg][64];   // [buf][segment][row*8 + centre]
+__global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
+  __shared__ __align__(16) double s_part[kPartBufs][kSeg][64];   // [buf][segment][row*8 + centre]
   __shared__ double s_xxc[kB];
   __shared__ long long s_pick[kB];
   __shared__ unsigned int s_hist[kNB + 1];
   const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
   if (nb <= 0) return;
-  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
-  const float4* X4 = reinterpret_cast<const float4*>(a.X);
-  const int lane_off = seg * (STEPS * 4) + kk;      // float4 offset of this lane inside a row
-
-  // B operands: centre g (padded with the last centre: min() is idempotent), this warp's segment
-  double breg[STEPS][4];
-  {
-    const long long pg = a.centers[min(g, nb - 1)];
-    const float4* cp = X4 + (size_t)pg * a.d4 + lane_off;
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      const float4 v = __ldg(cp + 4 * s);
-      breg[s][0] = (double)v.x;
-      breg[s][1] = (double)v.y;
-      breg[s][2] = (double)v.z;
-      breg[s][3] = (double)v.w;
-    }
-  }
+  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
   if (threadIdx.x < kB) {
-    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];
+    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];  // pad with the last centre: min() is idempotent
     s_xxc[threadIdx.x] = a.xx[p];
     s_pick[threadIdx.x] = p;
   }
-  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
-  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
-  int rule = 0;
-  if (a.ctl) {
-    rule = a.ctl->rule;
-    wd = a.ctl->wd;
-    wu = a.ctl->wu;
-    if (do_hist) {
-      h_lo = a.ctl->U - a.ctl->W;
-      h_inv = (double)kNB / a.ctl->W;
-      for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
-    }
-  }
+  if (do_hist)
+    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
   __syncthreads();
 
   const long long ntiles = (a.hi - a.lo + 7) / 8;
-  auto row_ptr = [&](long long t) {
-    const long long row = min(a.lo + t * 8 + g, a.hi - 1);   // rows past the end re-read the last row
-    return X4 + (size_t)row * a.d4 + lane_off;
-  };
-  long long t = blockIdx.x;
-  float4 ring[STEPS];
-  if (t < ntiles) {
-    const float4* p0 = row_ptr(t);
+  const long long nt = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < kSeg) {
+    // ------------------------------------------------------------------ compute warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int seg = warp, g = lane >> 2, kk = lane & 3;
+    const float4* X4 = reinterpret_cast<const float4*>(a.X);
+    const int lane_off = seg * (STEPS * 4) + kk;      // float4 offset of this lane inside a row
+    double breg[STEPS][4];
+    {
+      const long long pg = a.centers[min(g, nb - 1)];
+      const float4* cp = X4 + (size_t)pg * a.d4 + lane_off;
 #pragma unroll
-    for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(p0 + 4 * s);
-  }
-  int buf = 0;
-  for (; t < ntiles; t += gridDim.x) {
-    const long long tn = t + gridDim.x;
-    const bool has_next = tn < ntiles;
-    const float4* np = row_ptr(has_next ? tn : t);
-    // this warp finishes row `seg` of the tile: fetch its state early (latency hidden by the MMAs)
-    const long long i = a.lo + t * 8 + seg;
-    const bool live = i < a.hi;
+      for (int s = 0; s < STEPS; ++s) {
+        const float4 v = __ldg(cp + 4 * s);
+        breg[s][0] = (double)v.x;
+        breg[s][1] = (double)v.y;
+        breg[s][2] = (double)v.z;
+        breg[s][3] = (double)v.w;
+      }
+    }
+    auto row_ptr = [&](long long t) {
+      const long long row = min(a.lo + t * 8 + g, a.hi - 1);   // rows past the end re-read the last row
+      return X4 + (size_t)row * a.d4 + lane_off;
+    };
+    float4 ring[STEPS];
+    if (nt > 0) {
+      const float4* p0 = row_ptr(blockIdx.x);
+#pragma unroll
+      for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(p0 + 4 * s);
+    }
+    for (long long k = 0; k < nt; ++k) {
+      const long long t = blockIdx.x + k * gridDim.x;
+      const bool has_next = k + 1 < nt;
+      const float4* np = row_ptr(has_next ? t + gridDim.x : t);
+      double c[4][2];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+#pragma unroll
+      for (int s = 0; s < STEPS; ++s) {
+        const float4 x = ring[s];
+        if (has_next) ring[s] = ldg_stream(np + 4 * s);
+        dmma(c[0], (double)x.x, breg[s][0]);
+        dmma(c[1], (double)x.y, breg[s][1]);
+        dmma(c[2], (double)x.z, breg[s][2]);
+        dmma(c[3], (double)x.w, breg[s][3]);
+      }
+      const int b = (int)(k % kPartBufs);
+      if (k >= kPartBufs) named_sync(1 + kPartBufs + b, kWsThreads);   // buffer released by the epilogue
+      // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
+      *reinterpret_cast<double2*>(&s_part[b][seg][lane * 2]) =
+          make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
+      __threadfence_block();
+      named_arrive(1 + b, kWsThreads);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int ew = warp - kSeg;                 // 0..3: rows 2ew, 2ew+1 of every tile
+    const int r = 2 * ew + (lane >> 3), j = lane & 7;
+    const bool worker = lane < 16;
+    double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
+    int rule = 0;
+    if (a.ctl) {
+      rule = a.ctl->rule;
+      wd = a.ctl->wd;
+      wu = a.ctl->wu;
+      if (do_hist) {
+        h_lo = a.ctl->U - a.ctl->W;
+        h_inv = (double)kNB / a.ctl->W;
+      }
+    }
+    const double xxc = s_xxc[j];
+    const long long pick = s_pick[j];
+    // state of the row this lane group finishes, fetched one tile ahead
     double xxi = 0.0, mi = 0.0, ui = 0.0;
-    if (live && lane == 0) {
-      xxi = a.xx[i];
-      mi = a.m[i];
-      if (a.unc) ui = a.unc[i];
-    }
-    double c[4][2];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      const float4 x = ring[s];
-      if (has_next) ring[s] = ldg_stream(np + 4 * s);
-      dmma(c[0], (double)x.x, breg[s][0]);
-      dmma(c[1], (double)x.y, breg[s][1]);
-      dmma(c[2], (double)x.z, breg[s][2]);
-      dmma(c[3], (double)x.w, breg[s][3]);
-    }
-    // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
-    *reinterpret_cast<double2*>(&s_part[buf][seg][lane * 2]) =
-        make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
-    __syncthreads();
-    if (live) {   // warp-uniform
-      xxi = __shfl_sync(0xffffffffu, xxi, 0);
+    auto fetch = [&](long long k) {
+      const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
+      if (k < nt && worker && i < a.hi) {
+        xxi = a.xx[i];
+        if (j == 0) {
+          mi = a.m[i];
+          if (a.unc) ui = a.unc[i];
+        }
+      }
+    };
+    fetch(0);
+    for (long long k = 0; k < nt; ++k) {
+      const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
+      const bool live = worker && i < a.hi;
+      const double xxi_c = xxi, mi_c = mi, ui_c = ui;
+      fetch(k + 1);
+      const int b = (int)(k % kPartBufs);
+      named_sync(1 + b, kWsThreads);
       double dm = INFINITY;
       bool mine = false;
-      if (lane < kB) {
-        const double dot = combine8(&s_part[buf][0][seg * 8 + lane], 64);
-        dm = dist_from_dot(dot, xxi, s_xxc[lane]);
-        mine = s_pick[lane] == i;
+      if (live) {
+        const double dot = combine8(&s_part[b][0][r * 8 + j], 64);
+        dm = dist_from_dot(dot, xxi_c, xxc);
+        mine = pick == i;
       }
+      if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + b, kWsThreads);   // partials consumed
       dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 1));
       dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 2));
       dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 4));
-      const bool picked = __any_sync(0xffffffffu, mine);
-      if (lane == 0) {
-        const double dmin = fmin(mi, dm);
+      const unsigned pm = __ballot_sync(0xffffffffu, mine);
+      if (live && j == 0) {
+        const bool picked = ((pm >> (lane & 24)) & 0xffu) != 0u;
+        const double dmin = fmin(mi_c, dm);
         a.m[i] = dmin;
         if (a.unc) {
-          double u = ui;
+          double u = ui_c;
           if (picked) {
             u = 0.0;  // uncertainty[ind] = 0  (:848)
             a.unc[i] = 0.0;
@@ -552,15 +592,14 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pass_kernel_reg(PassArgs a) {
           if (do_hist) {
             const double fb = (sc - h_lo) * h_inv;
             if (fb >= 0.0) {
-              const int b = (int)fmin(fb, (double)(kNB - 1));
-              atomicAdd(&s_hist[b], 1u);
+              const int hb = (int)fmin(fb, (double)(kNB - 1));
+              atomicAdd(&s_hist[hb], 1u);
               atomicAdd(&s_hist[kNB], 1u);
             }
           }
         }
       }
     }
-    buf ^= 1;
   }
   __syncthreads();
   if (do_hist) {
@@ -1095,7 +1134,7 @@ static int launch_pass(PassArgs& a, cudaStream_t stream) {
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
-  if (a.d4 == kSeg * 4 * 16) pass_kernel_reg<16><<<sm_count(), kSeg * 32, 0, stream>>>(a);          // d = 2048
+  if (a.d4 == kSeg * 4 * 16) pass_kernel_ws<16><<<sm_count(), kWsThreads, 0, stream>>>(a);        // d = 2048
   else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   VQ_LAUNCHED();

@@ -10,7 +10,7 @@ from vatlq import ops, synth
 
 lib = vatlq._lib.lib()
 dev = "cuda:0"
-for rows, k in ((170000, 160), (21250, 400)):
+for rows, k in ((170000, 160), (21250, 400)):  # run under `timeout -s KILL`
     X = synth.device_embeddings(rows, dev, seed=2)
     unc = torch.rand(rows, dtype=torch.float64, device=dev)
     ops.coreset_select(X, unc, [], 16, 0.6, 0.01, batch=8)

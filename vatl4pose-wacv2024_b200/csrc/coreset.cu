@@ -437,9 +437,10 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
 //     register ring keeps a whole tile per lane in flight), four fp32->fp64 converts, four
 //     DMMAs.  A tile ends with one 16-byte shared store of the segment's partial dots and a
 //     non-blocking bar.arrive — compute warps never wait for anything but their own loads.
-//   * 4 EPILOGUE warps consume the partials through a 4-deep ring of named barriers: split-K
-//     reduction in the canonical order, distance, running minimum, unc/score update, histogram.
-// setmaxnreg moves registers from the epilogue warpgroup (40) to the compute warpgroups (232).
+//   * 4 EPILOGUE warps, one per partial buffer (tile k -> warp k mod 4, a pair of named barriers
+//     per buffer): split-K reduction in the canonical order, distance, running minimum,
+//     unc/score update, histogram.  Four tile-times per iteration hide their global latency.
+// setmaxnreg moves registers from the epilogue warpgroup (40) to the compute warpgroups (232): 8*32*232 + 4*32*40 = the 168*384 the CTA owns.
 constexpr int kPartBufs = 4;
 constexpr int kWsThreads = (kSeg + 4) * 32;   // 8 compute + 4 epilogue warps
 
@@ -519,19 +520,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
         dmma(c[3], (double)x.w, breg[s][3]);
       }
       const int b = (int)(k % kPartBufs);
-      if (k >= kPartBufs) named_sync(1 + kPartBufs + b, kWsThreads);   // buffer released by the epilogue
+      if (k >= kPartBufs) named_sync(1 + kPartBufs + b, kSeg * 32 + 32);   // buffer released by its epilogue warp
       // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
       *reinterpret_cast<double2*>(&s_part[b][seg][lane * 2]) =
           make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
       __threadfence_block();
-      named_arrive(1 + b, kWsThreads);
+      named_arrive(1 + b, kSeg * 32 + 32);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // epilogue warp ew owns partial buffer ew, i.e. tiles k = ew, ew+4, ...: four tile-times per
+    // iteration, so the row state fetched one iteration ahead is always there in time.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    const int ew = warp - kSeg;                 // 0..3: rows 2ew, 2ew+1 of every tile
-    const int r = 2 * ew + (lane >> 3), j = lane & 7;
-    const bool worker = lane < 16;
+    const int ew = warp - kSeg;
+    const int r = lane >> 2, kk = lane & 3;     // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
     double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
     int rule = 0;
     if (a.ctl) {
@@ -543,42 +545,36 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
         h_inv = (double)kNB / a.ctl->W;
       }
     }
-    const double xxc = s_xxc[j];
-    const long long pick = s_pick[j];
-    // state of the row this lane group finishes, fetched one tile ahead
+    const double xxc0 = s_xxc[2 * kk], xxc1 = s_xxc[2 * kk + 1];
+    const long long pick0 = s_pick[2 * kk], pick1 = s_pick[2 * kk + 1];
     double xxi = 0.0, mi = 0.0, ui = 0.0;
     auto fetch = [&](long long k) {
       const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
-      if (k < nt && worker && i < a.hi) {
+      if (k < nt && i < a.hi) {
         xxi = a.xx[i];
-        if (j == 0) {
+        if (kk == 0) {
           mi = a.m[i];
           if (a.unc) ui = a.unc[i];
         }
       }
     };
-    fetch(0);
-    for (long long k = 0; k < nt; ++k) {
+    fetch(ew);
+    for (long long k = ew; k < nt; k += kPartBufs) {
       const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
-      const bool live = worker && i < a.hi;
+      const bool live = i < a.hi;
       const double xxi_c = xxi, mi_c = mi, ui_c = ui;
-      fetch(k + 1);
-      const int b = (int)(k % kPartBufs);
-      named_sync(1 + b, kWsThreads);
-      double dm = INFINITY;
-      bool mine = false;
-      if (live) {
-        const double dot = combine8(&s_part[b][0][r * 8 + j], 64);
-        dm = dist_from_dot(dot, xxi_c, xxc);
-        mine = pick == i;
-      }
-      if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + b, kWsThreads);   // partials consumed
+      fetch(k + kPartBufs);
+      named_sync(1 + ew, kSeg * 32 + 32);
+      // (one centre at a time: the epilogue warpgroup lives in 40 registers)
+      const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
+      const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
+      if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
+      double dm = fmin(dist_from_dot(dot0, xxi_c, xxc0), dist_from_dot(dot1, xxi_c, xxc1));
       dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 1));
       dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 2));
-      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 4));
-      const unsigned pm = __ballot_sync(0xffffffffu, mine);
-      if (live && j == 0) {
-        const bool picked = ((pm >> (lane & 24)) & 0xffu) != 0u;
+      const unsigned pm = __ballot_sync(0xffffffffu, live && (pick0 == i || pick1 == i));
+      if (live && kk == 0) {
+        const bool picked = ((pm >> (lane & 28)) & 0xfu) != 0u;
         const double dmin = fmin(mi_c, dm);
         a.m[i] = dmin;
         if (a.unc) {

@@ -10,7 +10,7 @@ from vatlq import ops, synth
 
 lib = vatlq._lib.lib()
 dev = "cuda:0"
-for rows, k in ((170000, 160), (21250, 400)):  # run under `timeout -s KILL`
+for rows, k in ((170000, 800), (21250, 800)):  # run under `timeout -s KILL`
     X = synth.device_embeddings(rows, dev, seed=2)
     unc = torch.rand(rows, dtype=torch.float64, device=dev)
     ops.coreset_select(X, unc, [], 16, 0.6, 0.01, batch=8)
@@ -26,5 +26,5 @@ for rows, k in ((170000, 160), (21250, 400)):  # run under `timeout -s KILL`
     lib.vatlq_profile_passes(0)
     us = ms.value / max(n.value, 1) * 1e3
     print(f"{os.path.basename(os.environ.get('VATLQ_LIB', 'default'))}: rows={rows} pass={us:.1f} us  read={rows * 2048 * 4 / us / 1e3:.0f} GB/s "
-          f"fma={rows * 2048 * 8 / us / 1e6:.2f} T/s  total={e0.elapsed_time(e1):.1f} ms for {k} picks ({st.passes} passes)")
+          f"fma={rows * 2048 * 8 / us / 1e6:.2f} T/s  total={e0.elapsed_time(e1):.1f} ms for {k} picks ({st.passes} passes)\n   {st}")
     del X

@@ -12,6 +12,11 @@
 // surviving candidate still scores >= theta it beats every non-candidate (all < theta), ties
 // resolving to the lowest index exactly like np.argmax.  One pass over X then applies up to
 // kB picks at once, reading every row of X from HBM once instead of kB times.
+//
+// A round is three kernels: pairs (candidate x candidate distances) -> plan (replays the greedy
+// rule on the candidates, emits <= kB picks, chooses the next theta from the score histogram)
+// -> pass (applies the picks to every owned row; its epilogue lists the next candidates, the
+// exact arg-max for the fallback and the next histogram, so no separate filter pass exists).
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -40,7 +45,8 @@ struct RankBlock {  // the all-gather unit: one per rank per round
   double smax;      // exact maximum score of the owned rows ...
   long long smax_idx;  // ... and its lowest index
   long long inwin;  // owned rows inside the histogram window
-  long long pad[3];
+  long long mode;   // how theta was chosen: 0 no list requested, 1 from the histogram, 2 even the top bin overflows
+  long long pad[2];
   long long idx[kCapL];
   double m[kCapL];
   double unc[kCapL];
@@ -56,6 +62,8 @@ struct Ctl {
   int maxb, pad1;   // picks per pass allowed (1 = GEMV form: plain argmax every round)
   double wd, wu;    // score = wd*min_d + wu*unc
   double U, W;      // histogram window [U-W, U]; W <= 0: no window yet
+  double theta_emit;   // the pass lists every owned row whose new score is >= theta_emit (+inf: none)
+  int emit_mode, pad2; // RankBlock::mode of that list
   unsigned int filter_ticket, pad0;
   long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
 };
@@ -247,7 +255,77 @@ struct PassArgs {
   int n_centers_imm;
   Ctl* ctl;                  // null for initialisation passes
   unsigned int* hist;        // null: no histogram
+  RankBlock* send;           // null: do not list candidates / arg-max (initialisation passes)
+  Best* partial;             // per-CTA arg-max scratch (gridDim entries)
+  double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
 };
+
+// ---- what the epilogue of a pass leaves behind for the next round -------------------------
+// every owned row: running arg-max of the new scores; rows with score >= theta_emit are listed
+__device__ __forceinline__ void emit_row(RankBlock* send, double theta_emit, long long i, double dmin, double u,
+                                         double sc, Best& best) {
+  if (better(sc, i, best.s, best.i)) {
+    best.s = sc;
+    best.i = i;
+  }
+  if (sc >= theta_emit) {
+    const unsigned long long pos = atomicAdd((unsigned long long*)&send->count, 1ULL);
+    if (pos < (unsigned long long)kCapL) {
+      send->idx[pos] = i;
+      send->m[pos] = dmin;
+      send->unc[pos] = u;
+      send->score[pos] = sc;
+    }
+  }
+}
+
+// flush the CTA's histogram, reduce the arg-max over the CTA, and let the last CTA of the grid
+// finish the rank's block header (every thread of the CTA calls this)
+__device__ void publish_pass(const PassArgs& a, Best best, bool do_hist, const unsigned int* s_hist) {
+  __shared__ Best s_best[32];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+  if (do_hist) {
+    for (int b = tid; b < kNB + 1; b += blockDim.x)
+      if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
+  }
+  if (a.send == nullptr) return;
+  best = warp_best(best);
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < nw; ++k)
+      if (better(s_best[k].s, s_best[k].i, best.s, best.i)) best = s_best[k];
+    a.partial[blockIdx.x] = best;
+    __threadfence();
+    s_last = (atomicAdd(&a.ctl->filter_ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    Best b{-INFINITY, 0x7fffffffffffffffLL};
+    for (int k = tid; k < (int)gridDim.x; k += blockDim.x) {
+      Best q;
+      q.s = ((volatile Best*)a.partial)[k].s;
+      q.i = ((volatile Best*)a.partial)[k].i;
+      if (better(q.s, q.i, b.s, b.i)) b = q;
+    }
+    b = warp_best(b);
+    __syncthreads();
+    if ((tid & 31) == 0) s_best[tid >> 5] = b;
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < nw; ++k)
+        if (better(s_best[k].s, s_best[k].i, b.s, b.i)) b = s_best[k];
+      a.send->smax = b.s;
+      a.send->smax_idx = b.i;
+      a.send->theta = a.ctl->theta_emit;
+      a.send->mode = a.ctl->emit_mode;
+      a.send->inwin = do_hist ? (long long)((volatile unsigned int*)a.hist)[kNB] : 0;
+      a.ctl->filter_ticket = 0;
+    }
+  }
+}
 
 constexpr int kTeams = kPassThreads / 32 / kSeg;   // 2 teams of 8 warps
 
@@ -274,12 +352,14 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
     }
   }
   const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
-  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
+  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0, theta_emit = INFINITY;
   int rule = 0;
+  Best best{-INFINITY, 0x7fffffffffffffffLL};
   if (a.ctl) {
     rule = a.ctl->rule;
     wd = a.ctl->wd;
     wu = a.ctl->wu;
+    theta_emit = a.ctl->theta_emit;
     if (do_hist) {
       h_lo = a.ctl->U - a.ctl->W;
       h_inv = (double)kNB / a.ctl->W;
@@ -333,6 +413,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
           }
           const double sc = score_of(rule, wd, wu, dmin, u);
           a.score[i] = sc;
+          if (a.send) emit_row(a.send, theta_emit, i, dmin, u, sc, best);
           if (do_hist) {
             const double fb = (sc - h_lo) * h_inv;
             if (fb >= 0.0) {
@@ -423,10 +504,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
     }
   }
   __syncthreads();
-  if (do_hist) {
-    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x)
-      if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
-  }
+  publish_pass(a, best, do_hist, s_hist);
 }
 
 // ---------------------------------------------------------------- the pass over X, fast path
@@ -438,12 +516,13 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
 //     DMMAs.  A tile ends with one 16-byte shared store of the segment's partial dots and a
 //     non-blocking bar.arrive — compute warps never wait for anything but their own loads.
 //   * 4 EPILOGUE warps, one per partial buffer (tile k -> warp k mod 4, a pair of named barriers
-//     per buffer): split-K reduction in the canonical order, distance, running minimum,
-//     unc/score update, histogram.  Four tile-times per iteration hide their global latency.
+//     per buffer): split-K reduction in the canonical order, 8x8 dot products to global memory
+//     (64 B per row, < 1 % of the traffic); apply_kernel finishes the rows.
 // setmaxnreg moves registers from the epilogue warpgroup (40) to the compute warpgroups (232): 8*32*232 + 4*32*40 = the 168*384 the CTA owns.
 constexpr int kPartBufs = 4;
 constexpr int kWsThreads = (kSeg + 4) * 32;   // 8 compute + 4 epilogue warps
 
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -454,25 +533,13 @@ __device__ __forceinline__ void named_arrive(int id, int count) {
 template <int STEPS>
 __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
   __shared__ __align__(16) double s_part[kPartBufs][kSeg][64];   // [buf][segment][row*8 + centre]
-  __shared__ double s_xxc[kB];
-  __shared__ long long s_pick[kB];
-  __shared__ unsigned int s_hist[kNB + 1];
   const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
   if (nb <= 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
-  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
-  if (threadIdx.x < kB) {
-    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];  // pad with the last centre: min() is idempotent
-    s_xxc[threadIdx.x] = a.xx[p];
-    s_pick[threadIdx.x] = p;
-  }
-  if (do_hist)
-    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
-  __syncthreads();
 
   const long long ntiles = (a.hi - a.lo + 7) / 8;
-  const long long nt = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nt = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
   if (warp < kSeg) {
     // ------------------------------------------------------------------ compute warps
@@ -482,7 +549,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
     const int lane_off = seg * (STEPS * 4) + kk;      // float4 offset of this lane inside a row
     double breg[STEPS][4];
     {
-      const long long pg = a.centers[min(g, nb - 1)];
+      const long long pg = a.centers[min(g, nb - 1)];   // pad with the last centre: min() is idempotent
       const float4* cp = X4 + (size_t)pg * a.d4 + lane_off;
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
@@ -493,20 +560,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
         breg[s][3] = (double)v.w;
       }
     }
-    auto row_ptr = [&](long long t) {
-      const long long row = min(a.lo + t * 8 + g, a.hi - 1);   // rows past the end re-read the last row
-      return X4 + (size_t)row * a.d4 + lane_off;
-    };
+    // this lane's rows are a.lo + g + 8 * (blockIdx.x + k * gridDim.x): a fixed stride apart.
+    // 32-bit float4 offsets from X (host checks n * d4 < 2^32) keep the loop state small: the
+    // 232 registers hold 128 of B operands, 64 of ring and 16 of accumulators.
+    unsigned ro = (unsigned)(min(a.lo + (long long)blockIdx.x * 8 + g, a.hi - 1) * a.d4 + lane_off);
+    const unsigned rstride = gridDim.x * 8u * (unsigned)a.d4;            // float4 between this lane's tiles
+    const unsigned rlast = (unsigned)((a.hi - 1) * a.d4 + lane_off);      // rows past the end re-read the last row
     float4 ring[STEPS];
     if (nt > 0) {
-      const float4* p0 = row_ptr(blockIdx.x);
 #pragma unroll
-      for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(p0 + 4 * s);
+      for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(X4 + ro + 4 * s);
     }
-    for (long long k = 0; k < nt; ++k) {
-      const long long t = blockIdx.x + k * gridDim.x;
+    const unsigned my_part = smem_addr(&s_part[0][seg][lane * 2]);
+    for (int k = 0; k < nt; ++k) {
       const bool has_next = k + 1 < nt;
-      const float4* np = row_ptr(has_next ? t + gridDim.x : t);
+      ro = min(ro + rstride, rlast);
+      const float4* np = X4 + ro;
       double c[4][2];
 #pragma unroll
       for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
@@ -519,89 +588,100 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
         dmma(c[2], (double)x.z, breg[s][2]);
         dmma(c[3], (double)x.w, breg[s][3]);
       }
-      const int b = (int)(k % kPartBufs);
+      const int b = k & (kPartBufs - 1);
       if (k >= kPartBufs) named_sync(1 + kPartBufs + b, kSeg * 32 + 32);   // buffer released by its epilogue warp
       // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
-      *reinterpret_cast<double2*>(&s_part[b][seg][lane * 2]) =
-          make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
-      __threadfence_block();
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_part + b * (unsigned)sizeof(s_part[0])),
+                   "d"(combine4(c[0][0], c[1][0], c[2][0], c[3][0])), "d"(combine4(c[0][1], c[1][1], c[2][1], c[3][1]))
+                   : "memory");
+      asm volatile("fence.acq_rel.cta;" ::: "memory");   // partials visible before the arrive is counted
       named_arrive(1 + b, kSeg * 32 + 32);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // epilogue warp ew owns partial buffer ew, i.e. tiles k = ew, ew+4, ...: four tile-times per
-    // iteration, so the row state fetched one iteration ahead is always there in time.
+    // epilogue warp ew owns partial buffer ew, i.e. tiles k = ew, ew+4, ...: it finishes the split-K
+    // sums in the canonical order and stores the 8x8 dot products of the tile (apply_kernel turns
+    // them into distances / scores).  Deliberately tiny: this warpgroup lives in 40 registers and
+    // anything it spilled would queue in front of the compute warps' global loads.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     const int ew = warp - kSeg;
-    const int r = lane >> 2, kk = lane & 3;     // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
-    double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0;
-    int rule = 0;
-    if (a.ctl) {
-      rule = a.ctl->rule;
-      wd = a.ctl->wd;
-      wu = a.ctl->wu;
-      if (do_hist) {
-        h_lo = a.ctl->U - a.ctl->W;
-        h_inv = (double)kNB / a.ctl->W;
-      }
-    }
-    const double xxc0 = s_xxc[2 * kk], xxc1 = s_xxc[2 * kk + 1];
-    const long long pick0 = s_pick[2 * kk], pick1 = s_pick[2 * kk + 1];
-    double xxi = 0.0, mi = 0.0, ui = 0.0;
-    auto fetch = [&](long long k) {
-      const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
-      if (k < nt && i < a.hi) {
-        xxi = a.xx[i];
-        if (kk == 0) {
-          mi = a.m[i];
-          if (a.unc) ui = a.unc[i];
-        }
-      }
-    };
-    fetch(ew);
-    for (long long k = ew; k < nt; k += kPartBufs) {
-      const long long i = a.lo + (blockIdx.x + k * gridDim.x) * 8 + r;
-      const bool live = i < a.hi;
-      const double xxi_c = xxi, mi_c = mi, ui_c = ui;
-      fetch(k + kPartBufs);
+    const int r = lane >> 2;                    // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
+    for (int k = ew; k < nt; k += kPartBufs) {
       named_sync(1 + ew, kSeg * 32 + 32);
-      // (one centre at a time: the epilogue warpgroup lives in 40 registers)
       const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
       const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
       if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
-      double dm = fmin(dist_from_dot(dot0, xxi_c, xxc0), dist_from_dot(dot1, xxi_c, xxc1));
-      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 1));
-      dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, 2));
-      const unsigned pm = __ballot_sync(0xffffffffu, live && (pick0 == i || pick1 == i));
-      if (live && kk == 0) {
-        const bool picked = ((pm >> (lane & 28)) & 0xfu) != 0u;
-        const double dmin = fmin(mi_c, dm);
-        a.m[i] = dmin;
-        if (a.unc) {
-          double u = ui_c;
-          if (picked) {
-            u = 0.0;  // uncertainty[ind] = 0  (:848)
-            a.unc[i] = 0.0;
-          }
-          const double sc = score_of(rule, wd, wu, dmin, u);
-          a.score[i] = sc;
-          if (do_hist) {
-            const double fb = (sc - h_lo) * h_inv;
-            if (fb >= 0.0) {
-              const int hb = (int)fmin(fb, (double)(kNB - 1));
-              atomicAdd(&s_hist[hb], 1u);
-              atomicAdd(&s_hist[kNB], 1u);
-            }
-          }
+      const long long row = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + r;   // relative to a.lo
+      if (a.lo + row < a.hi) *reinterpret_cast<double2*>(a.dots + row * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
+    }
+  }
+}
+
+// second half of the fast-path pass: one thread per owned row turns the kB dot products into
+// distances, the running minimum, unc/score, the candidate list, the histogram and the arg-max
+__global__ void __launch_bounds__(256) apply_kernel(PassArgs a) {
+  __shared__ double s_xxc[kB];
+  __shared__ long long s_pick[kB];
+  __shared__ unsigned int s_hist[kNB + 1];
+  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  if (nb <= 0) return;
+  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+  if (threadIdx.x < kB) {
+    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];
+    s_xxc[threadIdx.x] = a.xx[p];
+    s_pick[threadIdx.x] = p;
+  }
+  if (do_hist)
+    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
+  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0, theta_emit = INFINITY;
+  int rule = 0;
+  if (a.ctl) {
+    rule = a.ctl->rule;
+    wd = a.ctl->wd;
+    wu = a.ctl->wu;
+    theta_emit = a.ctl->theta_emit;
+    if (do_hist) {
+      h_lo = a.ctl->U - a.ctl->W;
+      h_inv = (double)kNB / a.ctl->W;
+    }
+  }
+  __syncthreads();
+  Best best{-INFINITY, 0x7fffffffffffffffLL};
+  for (long long i = a.lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi; i += (long long)gridDim.x * blockDim.x) {
+    const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
+    const double xxi = a.xx[i];
+    double dm = INFINITY;
+    bool picked = false;
+#pragma unroll
+    for (int q = 0; q < kB / 2; ++q) {
+      const double2 d2 = dp[q];
+      dm = fmin(dm, dist_from_dot(d2.x, xxi, s_xxc[2 * q]));
+      dm = fmin(dm, dist_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
+      picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
+    }
+    const double dmin = fmin(a.m[i], dm);
+    a.m[i] = dmin;
+    if (a.unc) {
+      double u = a.unc[i];
+      if (picked) {
+        u = 0.0;  // uncertainty[ind] = 0  (:848)
+        a.unc[i] = 0.0;
+      }
+      const double sc = score_of(rule, wd, wu, dmin, u);
+      a.score[i] = sc;
+      if (a.send) emit_row(a.send, theta_emit, i, dmin, u, sc, best);
+      if (do_hist) {
+        const double fb = (sc - h_lo) * h_inv;
+        if (fb >= 0.0) {
+          const int hb = (int)fmin(fb, (double)(kNB - 1));
+          atomicAdd(&s_hist[hb], 1u);
+          atomicAdd(&s_hist[kNB], 1u);
         }
       }
     }
   }
   __syncthreads();
-  if (do_hist) {
-    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x)
-      if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
-  }
+  publish_pass(a, best, do_hist, s_hist);
 }
 
 static size_t pass_smem_bytes(int S) {
@@ -619,92 +699,19 @@ __global__ void __launch_bounds__(256) score_init_kernel(long long lo, long long
   score[i] = ctl->first_round ? unc[i] : score_of(ctl->rule, ctl->wd, ctl->wu, m[i], unc[i]);
 }
 
-// ---------------------------------------------------------------- candidate filter
-__global__ void __launch_bounds__(256) filter_kernel(long long lo, long long hi, const double* __restrict__ m,
-                                                     const double* __restrict__ unc, const double* __restrict__ score,
-                                                     unsigned int* hist, Best* partial, RankBlock* out, Ctl* ctl) {
-  if (ctl->n_picked >= ctl->k) return;
-  __shared__ double s_theta;
+// ---------------------------------------------------------------- bootstrap: arg-max of the initial scores
+// Only before the first round: afterwards every pass leaves the block header behind itself.
+__global__ void __launch_bounds__(256) bootstrap_kernel(long long lo, long long hi, const double* __restrict__ score,
+                                                        Best* partial, RankBlock* out, Ctl* ctl) {
   __shared__ Best s_best[8];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x;
-  // theta from the score histogram the last pass left behind (identical in every CTA)
-  const double U = ctl->U, W = ctl->W;
-  const int target = max(1, kTarget / max(1, ctl->world));
-  const bool windowed = W > 0.0 && ctl->maxb > 1;
-  if (windowed) {
-    // suffix counts cum[b] = #rows in bins >= b: 256 threads x 4 bins, warp scan + 8 warp totals
-    __shared__ unsigned int s_wtot[8];
-    __shared__ int s_bstar[8], s_bfit[8];
-    const int lane = tid & 31, wp = tid >> 5;
-    unsigned int h[4], tot = 0;
-#pragma unroll
-    for (int c = 3; c >= 0; --c) {
-      tot += hist[tid * 4 + c];
-      h[c] = tot;                    // bins c..3 of this thread's chunk
-    }
-    unsigned int v = tot;            // inclusive suffix over the lanes of this warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
-      if (lane + o < 32) v += t;
-    }
-    if (lane == 0) s_wtot[wp] = v;
-    __syncthreads();
-    unsigned int run = v - tot;      // rows in bins of higher-indexed threads
-    for (int w = wp + 1; w < 8; ++w) run += s_wtot[w];
-    int bstar = -1;                  // highest bin whose suffix count reaches the target
-    int bfit = kNB;                  // lowest bin whose suffix count still fits the record capacity
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const unsigned int cum = run + h[e];
-      if (cum >= (unsigned)target) bstar = max(bstar, tid * 4 + e);
-      if (cum <= (unsigned)kCapL) bfit = min(bfit, tid * 4 + e);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      bstar = max(bstar, __shfl_xor_sync(0xffffffffu, bstar, o));
-      bfit = min(bfit, __shfl_xor_sync(0xffffffffu, bfit, o));
-    }
-    if (lane == 0) {
-      s_bstar[wp] = bstar;
-      s_bfit[wp] = bfit;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < 8; ++w) {
-        bstar = max(bstar, s_bstar[w]);
-        bfit = min(bfit, s_bfit[w]);
-      }
-      if (bstar < 0) bstar = 0;
-      double th;
-      if (bfit == kNB) th = INFINITY;  // even the top bin overflows: exact-argmax fallback
-      else {
-        const int b = max(bstar, bfit);
-        th = (b == 0) ? (U - W) : (U - W) + (double)b * (W / (double)kNB);
-      }
-      s_theta = th;
-    }
-  } else if (tid == 0) {
-    s_theta = INFINITY;
-  }
-  __syncthreads();
-  const double theta = s_theta;
   Best best{-INFINITY, 0x7fffffffffffffffLL};
   for (long long i = lo + (long long)blockIdx.x * blockDim.x + tid; i < hi; i += (long long)gridDim.x * blockDim.x) {
     const double s = score[i];
     if (better(s, i, best.s, best.i)) {
       best.s = s;
       best.i = i;
-    }
-    if (s >= theta) {
-      const unsigned long long pos = atomicAdd((unsigned long long*)&out->count, 1ULL);
-      if (pos < (unsigned long long)kCapL) {
-        out->idx[pos] = i;
-        out->m[pos] = m[i];
-        out->unc[pos] = unc[i];
-        out->score[pos] = s;
-      }
     }
   }
   best = warp_best(best);
@@ -722,32 +729,33 @@ __global__ void __launch_bounds__(256) filter_kernel(long long lo, long long hi,
     __threadfence();
     Best b{-INFINITY, 0x7fffffffffffffffLL};
     for (int k = tid; k < (int)gridDim.x; k += blockDim.x) {
-      Best p;
-      p.s = ((volatile Best*)partial)[k].s;
-      p.i = ((volatile Best*)partial)[k].i;
-      if (better(p.s, p.i, b.s, b.i)) b = p;
+      Best q;
+      q.s = ((volatile Best*)partial)[k].s;
+      q.i = ((volatile Best*)partial)[k].i;
+      if (better(q.s, q.i, b.s, b.i)) b = q;
     }
     b = warp_best(b);
+    __syncthreads();
     if ((tid & 31) == 0) s_best[tid >> 5] = b;
     __syncthreads();
     if (tid == 0) {
       for (int k = 1; k < 8; ++k)
         if (better(s_best[k].s, s_best[k].i, b.s, b.i)) b = s_best[k];
+      out->count = 0;
       out->smax = b.s;
       out->smax_idx = b.i;
-      out->theta = theta;
-      out->inwin = windowed ? (long long)hist[kNB] : 0;
+      out->theta = INFINITY;
+      out->mode = 0;
+      out->inwin = 0;
       ctl->filter_ticket = 0;
     }
-    // every CTA has consumed the histogram (it is read before the ticket): clear it
-    for (int k = tid; k < kNB + 1; k += blockDim.x) hist[k] = 0u;
   }
 }
 
 // ---------------------------------------------------------------- candidate bookkeeping
 struct CandView {
   int total;        // candidates over all ranks (records actually stored)
-  int fallback;     // 0 plan on candidates, 1 nothing listed, 2 overflow
+  int fallback;     // 0 plan on candidates, 1 nothing listed, 2 overflow, 3 no list was requested
   double theta;     // max over ranks
   int start[kMaxRanks + 1];
 };
@@ -756,16 +764,18 @@ __device__ __forceinline__ CandView view_of(const RankBlock* blocks, int world) 
   v.total = 0;
   v.fallback = 0;
   v.theta = -INFINITY;
-  bool overflow = false;
+  bool overflow = false, unlisted = false;
   for (int r = 0; r < world; ++r) {
     v.start[r] = v.total;
     const long long c = blocks[r].count;
-    if (c > kCapL) overflow = true;
+    if (c > kCapL || blocks[r].mode == 2) overflow = true;
+    if (blocks[r].mode == 0) unlisted = true;
     v.total += (int)min(c, (long long)kCapL);
     v.theta = fmax(v.theta, blocks[r].theta);
   }
   v.start[world] = v.total;
-  if (overflow || v.total > kCap || isinf(v.theta)) v.fallback = 2;
+  if (overflow || v.total > kCap) v.fallback = 2;
+  else if (unlisted || isinf(v.theta)) v.fallback = 3;
   else if (v.total == 0) v.fallback = 1;
   return v;
 }
@@ -818,6 +828,82 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
   }
 }
 
+// fast path (d == 8 * 16 * STEPS): the pass kernel's tile machine on the gathered candidates.
+// CTA (cb, y): the 8 candidates of column block cb are the centres (their 1/8 K-slices live in the
+// registers of the 8 warps), row tiles y, y + gridDim.y, ... of the candidate list stream through
+// a register ring (from L2 mostly: the rows were just touched by the pass).  After the split-K
+// exchange warp w finishes row w of the tile: lane j writes d(row, centre j).
+template <int STEPS>
+__global__ void __launch_bounds__(kSeg * 32, 1) pairs_kernel_reg(const float* __restrict__ X, int d4,
+                                                                 const double* __restrict__ xx, const RankBlock* blocks,
+                                                                 const Ctl* ctl, double* __restrict__ Dcc) {
+  if (ctl->n_picked >= ctl->k) return;
+  __shared__ __align__(16) double s_part[2][kSeg][64];
+  __shared__ double s_xxc[kB];
+  const int world = ctl->world;
+  const CandView v = view_of(blocks, world);
+  if (v.fallback) return;
+  const int col0 = blockIdx.x * kB;
+  if (col0 >= v.total) return;
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const int lane_off = seg * (STEPS * 4) + kk;
+  auto cand_row = [&](int pos) {
+    int r, q;
+    locate(v, world, min(pos, v.total - 1), r, q);
+    return blocks[r].idx[q];
+  };
+  double breg[STEPS][4];
+  {
+    const float4* cp = X4 + (size_t)cand_row(col0 + g) * d4 + lane_off;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 c4 = __ldg(cp + 4 * s);
+      breg[s][0] = (double)c4.x;
+      breg[s][1] = (double)c4.y;
+      breg[s][2] = (double)c4.z;
+      breg[s][3] = (double)c4.w;
+    }
+  }
+  if (threadIdx.x < kB) s_xxc[threadIdx.x] = xx[cand_row(col0 + threadIdx.x)];
+  const int ntiles = (v.total + 7) / 8;
+  int t = blockIdx.y;
+  float4 ring[STEPS];
+  if (t < ntiles) {
+    const float4* p0 = X4 + (size_t)cand_row(t * 8 + g) * d4 + lane_off;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) ring[s] = __ldg(p0 + 4 * s);
+  }
+  int buf = 0;
+  for (; t < ntiles; t += gridDim.y) {
+    const int tn = t + gridDim.y;
+    const bool has_next = tn < ntiles;
+    const float4* np = X4 + (size_t)cand_row((has_next ? tn : t) * 8 + g) * d4 + lane_off;
+    const int myrow = t * 8 + seg;                       // the row this warp finishes
+    const double xxi = (myrow < v.total) ? xx[cand_row(myrow)] : 0.0;
+    double c[4][2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 x = ring[s];
+      if (has_next) ring[s] = __ldg(np + 4 * s);
+      dmma(c[0], (double)x.x, breg[s][0]);
+      dmma(c[1], (double)x.y, breg[s][1]);
+      dmma(c[2], (double)x.z, breg[s][2]);
+      dmma(c[3], (double)x.w, breg[s][3]);
+    }
+    *reinterpret_cast<double2*>(&s_part[buf][seg][lane * 2]) =
+        make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
+    __syncthreads();
+    if (myrow < v.total && lane < kB && col0 + lane < v.total) {
+      const double dot = combine8(&s_part[buf][0][seg * 8 + lane], 64);
+      Dcc[(size_t)myrow * kCap + col0 + lane] = dist_from_dot(dot, xxi, s_xxc[lane]);
+    }
+    buf ^= 1;
+  }
+}
+
 // exact global argmax from the per-rank headers: always the correct next greedy pick
 __device__ void fallback_pick(const RankBlock* blocks, int world, int kind, RankBlock* send,
                               long long* __restrict__ out_idx, Ctl* ctl) {
@@ -844,9 +930,11 @@ __device__ void fallback_pick(const RankBlock* blocks, int world, int kind, Rank
     if (kind == 2) {
       ctl->stat_fallback_overflow += 1;
       W = (W > 0.0) ? W / 16.0 : b.s / 64.0;
-    } else {
+    } else if (kind == 1) {
       ctl->stat_fallback_empty += 1;
       W = (W > 0.0) ? fmin(b.s, W * 4.0) : b.s / 64.0;
+    } else if (!(W > 0.0)) {   // kind 3: no list was requested yet -> open the first window
+      W = b.s / 64.0;
     }
     if (!(W > 0.0)) W = b.s;
     ctl->W = W;
@@ -855,22 +943,103 @@ __device__ void fallback_pick(const RankBlock* blocks, int world, int kind, Rank
 }
 
 // ---------------------------------------------------------------- the planner: exact greedy on candidates
+// theta for the list the NEXT pass emits, from the histogram the PREVIOUS pass left behind
+// (scores only decrease, so the real list can only be shorter than the histogram says): the
+// highest bin edge whose suffix count reaches the target, raised until the list fits a block.
+// Called by the first 256 threads of the CTA with block-wide barriers around it.
+__device__ void choose_theta(const unsigned int* __restrict__ hist, double U, double W, int target, int tid,
+                             double* s_theta, int* s_mode) {
+  __shared__ unsigned int s_wtot[8];
+  __shared__ int s_bstar[8], s_bfit[8];
+  if (tid < 256) {
+    const int lane = tid & 31, wp = tid >> 5;
+    unsigned int h[4], tot = 0;
+#pragma unroll
+    for (int c = 3; c >= 0; --c) {
+      tot += hist[tid * 4 + c];
+      h[c] = tot;                    // bins c..3 of this thread's chunk
+    }
+    unsigned int v = tot;            // inclusive suffix over the lanes of this warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
+      if (lane + o < 32) v += t;
+    }
+    if (lane == 0) s_wtot[wp] = v;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    unsigned int run = v - tot;      // rows in bins of higher-indexed threads
+    for (int w = wp + 1; w < 8; ++w) run += s_wtot[w];
+    int bstar = -1;                  // highest bin whose suffix count reaches the target
+    int bfit = kNB;                  // lowest bin whose suffix count still fits the record capacity
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned int cum = run + h[e];
+      if (cum >= (unsigned)target) bstar = max(bstar, tid * 4 + e);
+      if (cum <= (unsigned)kCapL) bfit = min(bfit, tid * 4 + e);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      bstar = max(bstar, __shfl_xor_sync(0xffffffffu, bstar, o));
+      bfit = min(bfit, __shfl_xor_sync(0xffffffffu, bfit, o));
+    }
+    if (lane == 0) {
+      s_bstar[wp] = bstar;
+      s_bfit[wp] = bfit;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w) {
+        bstar = max(bstar, s_bstar[w]);
+        bfit = min(bfit, s_bfit[w]);
+      }
+      if (bstar < 0) bstar = 0;
+      if (bfit == kNB) {             // even the top bin overflows: exact-argmax rounds until the window shrinks
+        *s_theta = INFINITY;
+        *s_mode = 2;
+      } else {
+        const int bb = max(bstar, bfit);
+        *s_theta = (bb == 0) ? (U - W) : (U - W) + (double)bb * (W / (double)kNB);
+        *s_mode = 1;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, RankBlock* send, const double* __restrict__ Dcc,
-                                                    long long* __restrict__ out_idx, Ctl* ctl) {
-  __shared__ Best s_b[32];
-  __shared__ int s_pos[32];
-  __shared__ Best s_win;
-  __shared__ int s_winpos;
+                                                    unsigned int* hist, long long* __restrict__ out_idx, Ctl* ctl) {
+  __shared__ Best s_b[2][32];
+  __shared__ int s_pos[2][32];
+  __shared__ double s_theta;
+  __shared__ int s_mode;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (ctl->n_picked >= ctl->k) {
     if (tid == 0) ctl->nb = 0;
     return;
   }
   const int world = ctl->world;
+  // ---- theta of the list the coming pass emits (window the histogram was built with: the
+  // U, W this kernel has not updated yet), then clear the histogram for that pass
+  {
+    const double U0 = ctl->U, W0 = ctl->W;
+    const bool windowed = W0 > 0.0 && ctl->maxb > 1 && !ctl->first_round;
+    if (tid == 0) {
+      s_theta = INFINITY;
+      s_mode = 0;
+    }
+    __syncthreads();
+    if (windowed) choose_theta(hist, U0, W0, max(1, kTarget / max(1, world)), tid, &s_theta, &s_mode);
+    __syncthreads();
+    for (int k = tid; k < kNB + 1; k += blockDim.x) hist[k] = 0u;
+    if (tid == 0) {
+      ctl->theta_emit = s_theta;
+      ctl->emit_mode = s_mode;
+    }
+  }
   const CandView v = view_of(blocks, world);
   const int rule = ctl->rule;
   const double wd = ctl->wd, wu = ctl->wu;
   const long long remaining = ctl->k - ctl->n_picked;
+  __syncthreads();   // every thread has read the block headers before thread 0 may reset them
   if (v.fallback) {
     if (tid == 0) fallback_pick(blocks, world, v.fallback, send, out_idx, ctl);
     return;
@@ -887,8 +1056,10 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
     sc = blocks[r].score[s];
   }
   const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kB, ctl->maxb)), remaining);
+  const int nwarps = (v.total + 31) >> 5;   // warps that hold candidates
   int nb = 0;
   for (int b = 0; b < maxpicks; ++b) {
+    // block arg-max: warp butterflies, one barrier, every warp reduces the warp winners again
     Best me{sc, idx};
     int pos = tid;
 #pragma unroll
@@ -903,33 +1074,27 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
       }
     }
     if (lane == 0) {
-      s_b[warp] = me;
-      s_pos[warp] = pos;
+      s_b[b & 1][warp] = me;
+      s_pos[b & 1][warp] = pos;
     }
     __syncthreads();
-    if (warp == 0) {
-      Best w = s_b[lane];
-      int p = s_pos[lane];
+    Best win{-INFINITY, 0x7fffffffffffffffLL};
+    int wpos = 0;
+    if (lane < nwarps) {
+      win = s_b[b & 1][lane];
+      wpos = s_pos[b & 1][lane];
+    }
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const double s2 = __shfl_xor_sync(0xffffffffu, w.s, o);
-        const long long i2 = __shfl_xor_sync(0xffffffffu, w.i, o);
-        const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
-        if (better(s2, i2, w.s, w.i)) {
-          w.s = s2;
-          w.i = i2;
-          p = p2;
-        }
-      }
-      if (lane == 0) {
-        s_win = w;
-        s_winpos = p;
+    for (int o = 16; o; o >>= 1) {
+      const double s2 = __shfl_xor_sync(0xffffffffu, win.s, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, win.i, o);
+      const int p2 = __shfl_xor_sync(0xffffffffu, wpos, o);
+      if (better(s2, i2, win.s, win.i)) {
+        win.s = s2;
+        win.i = i2;
+        wpos = p2;
       }
     }
-    __syncthreads();
-    const Best win = s_win;
-    const int wpos = s_winpos;
-    __syncthreads();
     if (!(win.s >= v.theta)) {  // a non-candidate (score < theta) could be ahead now
       if (b == 0) {             // (only possible when the rank that set theta listed nothing)
         if (tid == 0) fallback_pick(blocks, world, 1, send, out_idx, ctl);
@@ -943,7 +1108,7 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
     }
     nb += 1;
     if (tid < v.total) {
-      m = fmin(m, Dcc[(size_t)tid * kCap + wpos]);
+      m = fmin(m, Dcc[(size_t)wpos * kCap + tid]);   // d is symmetric: the winner's row, coalesced
       if (tid == wpos) u = 0.0;
       sc = score_of(rule, wd, wu, m, u);
     }
@@ -951,12 +1116,13 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
   // best surviving candidate score -> upper bound of every score after the pass
   Best me{sc, idx};
   me = warp_best(me);
-  if (lane == 0) s_b[warp] = me;
+  __syncthreads();
+  if (lane == 0) s_b[0][warp] = me;
   __syncthreads();
   if (tid == 0) {
-    Best b = s_b[0];
+    Best b = s_b[0][0];
     for (int k = 1; k < 32; ++k)
-      if (better(s_b[k].s, s_b[k].i, b.s, b.i)) b = s_b[k];
+      if (better(s_b[0][k].s, s_b[0][k].i, b.s, b.i)) b = s_b[0][k];
     long long inwin = 0;
     for (int r = 0; r < world; ++r) inwin += blocks[r].inwin;
     const double U = ctl->U;
@@ -1048,7 +1214,7 @@ struct Comm {
 
 // ---------------------------------------------------------------- workspace layout
 struct WsLayout {
-  size_t xx, score, hist, partial, send, recv, dcc, ctl, total;
+  size_t xx, score, hist, partial, send, recv, dcc, ctl, dots, total;
 };
 static WsLayout ws_layout(long long n, int world) {
   WsLayout L;
@@ -1066,6 +1232,7 @@ static WsLayout ws_layout(long long n, int world) {
   L.send = take(sizeof(RankBlock));
   L.recv = take(sizeof(RankBlock) * (size_t)kMaxRanks);
   L.dcc = take((size_t)kCap * kCap * 8);
+  L.dots = take((size_t)n * kB * 8);
   L.total = o;
   return L;
 }
@@ -1123,17 +1290,26 @@ static int launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream
   return 0;
 }
 
-static int launch_pass(PassArgs& a, cudaStream_t stream) {
+static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
   static bool configured = false;
   if (!configured) {
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
-  if (a.d4 == kSeg * 4 * 16) pass_kernel_ws<16><<<sm_count(), kWsThreads, 0, stream>>>(a);        // d = 2048
+  if (ev0) cudaEventRecord(ev0, stream);
+  const bool fast = a.d4 == kSeg * 4 * 16 && a.dots != nullptr && (unsigned long long)a.n * a.d4 < (1ULL << 32);   // d = 2048
+  if (fast) pass_kernel_ws<16><<<sm_count(), kWsThreads, 0, stream>>>(a);
   else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
+  if (ev1) cudaEventRecord(ev1, stream);
   VQ_LAUNCHED();
+  if (fast) {
+    const long long rows = a.hi - a.lo;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 255) / 256, (long long)sm_count() * 8));
+    apply_kernel<<<grid, 256, 0, stream>>>(a);
+    VQ_LAUNCHED();
+  }
   return 0;
 }
 
@@ -1155,6 +1331,7 @@ extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_
   for (int64_t c0 = 0; c0 < n_labeled; c0 += kB) {
     PassArgs a{};
     a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.dots = (double*)(w + L.dots);
     a.unc = nullptr; a.score = nullptr; a.centers = (const long long*)labeled + c0; a.n_centers = nullptr;
     a.n_centers_imm = (int)std::min<int64_t>(kB, n_labeled - c0); a.ctl = nullptr; a.hist = nullptr;
     if (int e = launch_pass(a, stream)) return e;
@@ -1211,13 +1388,19 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
 
   const int own = (int)std::min<int64_t>(row_hi - row_lo, 1LL << 30);
   int fgrid = std::max(1, std::min(sm_count() * 4, (own + 255) / 256));
-  VQ_REQUIRE(fgrid <= 4096, "filter grid too large");
+  VQ_REQUIRE(fgrid <= 4096 && sm_count() <= 4096, "grid too large for the arg-max scratch");
   const size_t pairs_smem = G.smem;
+  const bool fast_d = (G.d4 == kSeg * 4 * 16);   // d = 2048: register-resident centres
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     pairs_cfg = true;
   }
+  auto fill_pass = [&](PassArgs& a) {
+    a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
+    a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.n_centers_imm = 0; a.ctl = ctl;
+    a.hist = (nbk > 1) ? hist : nullptr; a.send = send; a.partial = partial; a.dots = (double*)(w + L.dots);
+  };
 
   if (n_labeled == 0 && rule == 2) {
     // apply the given first pick directly (one pass), then continue with argmax(min_d)
@@ -1226,8 +1409,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     VQ_CUDA(cudaMemcpyAsync(ctl, &h2, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
     VQ_CUDA(cudaMemcpyAsync(out_idx, &first_pick, 8, cudaMemcpyHostToDevice, stream));
     PassArgs a{};
-    a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
-    a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl; a.hist = hist;
+    fill_pass(a);
+    a.send = nullptr;   // the bootstrap below computes the arg-max of the scores this pass writes
     if (int e = launch_pass(a, stream)) return e;
   } else {
     const long long cnt = row_hi - row_lo;
@@ -1236,9 +1419,12 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       VQ_LAUNCHED();
     }
   }
+  // block header of round 0 (no list, exact arg-max); later headers come from the passes
+  bootstrap_kernel<<<fgrid, 256, 0, stream>>>(row_lo, row_hi, score, partial, send, ctl);
+  VQ_LAUNCHED();
 
-  // rounds: filter -> [all-gather] -> pairs -> plan -> pass.  The host only learns the pick
-  // count every `chunk` rounds; kernels of surplus rounds exit on n_picked >= k.
+  // rounds: [all-gather] -> pairs -> plan -> pass.  The host only learns the pick count every
+  // `chunk` rounds; kernels of surplus rounds exit on n_picked >= k.
   long long picked = (n_labeled == 0 && rule == 2) ? 1 : 0;
   long long rounds_done = 0;
   long long passes_seen = (n_labeled == 0 && rule == 2) ? 1 : 0;
@@ -1252,8 +1438,6 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     long long chunk = (long long)((double)remaining / std::max(1.0, per_round)) + 2;
     chunk = std::max<long long>(4, std::min<long long>(chunk, 256));
     for (long long it = 0; it < chunk && rc == 0; ++it) {
-      filter_kernel<<<fgrid, 256, 0, stream>>>(row_lo, row_hi, min_d, unc, score, hist, partial, send, ctl);
-      g_launches.fetch_add(1);
       if (world > 1) {
         const int e = g_nccl.AllGather(send, recv, sizeof(RankBlock), /*ncclChar*/ 0, comm->nccl, stream);
         if (e != 0) {
@@ -1263,23 +1447,22 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         }
       }
       if (nbk > 1) {
-        dim3 pg(kCap / kB, 4);
-        pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
+        if (fast_d) {
+          dim3 pg(kCap / kB, 4);
+          pairs_kernel_reg<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, recv, ctl, Dcc);
+        } else {
+          dim3 pg(kCap / kB, 4);
+          pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
+        }
         g_launches.fetch_add(1);
       }
-      plan_kernel<<<1, kCap, 0, stream>>>(recv, send, Dcc, (long long*)out_idx, ctl);
+      plan_kernel<<<1, kCap, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
       g_launches.fetch_add(1);
       PassArgs a{};
-      a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
-      a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.ctl = ctl;
-      a.hist = (nbk > 1) ? hist : nullptr;
-        const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
-      if (timed) cudaEventRecord(g_prof.ev[g_prof.used], stream);
-      rc = launch_pass(a, stream);
-      if (timed) {
-        cudaEventRecord(g_prof.ev[g_prof.used + 1], stream);
-        g_prof.used += 2;
-      }
+      fill_pass(a);
+      const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+      rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
+      if (timed) g_prof.used += 2;
     }
     if (rc) break;
     rounds_done += chunk;

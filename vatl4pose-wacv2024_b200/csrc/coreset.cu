@@ -94,11 +94,13 @@ __device__ __forceinline__ double score_of(int rule, double wd, double wu, doubl
   return m;                                                              // :832
 }
 
-__device__ __forceinline__ double dist_from_dot(double dot, double xxi, double xxc) {
+__device__ __forceinline__ double sq_from_dot(double dot, double xxi, double xxc) {
   double t = __dmul_rn(-2.0, dot);
   t = __dadd_rn(t, xxi);
-  t = __dadd_rn(t, xxc);
-  return sqrt(fmax(t, 0.0));
+  return __dadd_rn(t, xxc);
+}
+__device__ __forceinline__ double dist_from_dot(double dot, double xxi, double xxc) {
+  return sqrt(fmax(sq_from_dot(dot, xxi, xxc), 0.0));
 }
 
 // ---- the fp64 tensor-core tile --------------------------------------------------------------
@@ -650,16 +652,18 @@ __global__ void __launch_bounds__(256) apply_kernel(PassArgs a) {
   for (long long i = a.lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi; i += (long long)gridDim.x * blockDim.x) {
     const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
     const double xxi = a.xx[i];
-    double dm = INFINITY;
+    // min_j sqrt(max(t_j, 0)) == sqrt(max(min_j t_j, 0)) bit for bit (sqrt is monotone and correctly
+    // rounded), so one square root per row instead of kB
+    double tm = INFINITY;
     bool picked = false;
 #pragma unroll
     for (int q = 0; q < kB / 2; ++q) {
       const double2 d2 = dp[q];
-      dm = fmin(dm, dist_from_dot(d2.x, xxi, s_xxc[2 * q]));
-      dm = fmin(dm, dist_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
+      tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
+      tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
       picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
     }
-    const double dmin = fmin(a.m[i], dm);
+    const double dmin = fmin(a.m[i], sqrt(fmax(tm, 0.0)));
     a.m[i] = dmin;
     if (a.unc) {
       double u = a.unc[i];
@@ -1005,10 +1009,14 @@ __device__ void choose_theta(const unsigned int* __restrict__ hist, double U, do
   }
 }
 
-__global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, RankBlock* send, const double* __restrict__ Dcc,
-                                                    unsigned int* hist, long long* __restrict__ out_idx, Ctl* ctl) {
-  __shared__ Best s_b[2][32];
-  __shared__ int s_pos[2][32];
+constexpr int kPlanThreads = 256;
+constexpr int kPerThread = kCap / kPlanThreads;   // candidates per planner thread (strided: c = tid + 256 j)
+
+__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blocks, RankBlock* send,
+                                                            const double* __restrict__ Dcc, unsigned int* hist,
+                                                            long long* __restrict__ out_idx, Ctl* ctl) {
+  __shared__ Best s_b[2][8];
+  __shared__ int s_pos[2][8];
   __shared__ double s_theta;
   __shared__ int s_mode;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1039,29 +1047,43 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
   const int rule = ctl->rule;
   const double wd = ctl->wd, wu = ctl->wu;
   const long long remaining = ctl->k - ctl->n_picked;
-  __syncthreads();   // every thread has read the block headers before thread 0 may reset them
+  const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kB, ctl->maxb)), remaining);
+  __syncthreads();   // every thread has read the block headers / ctl before thread 0 may change them
   if (v.fallback) {
     if (tid == 0) fallback_pick(blocks, world, v.fallback, send, out_idx, ctl);
     return;
   }
-  // one candidate per thread
-  long long idx = 0x7fffffffffffffffLL;
-  double m = 0.0, u = 0.0, sc = -INFINITY;
-  if (tid < v.total) {
-    int r, s;
-    locate(v, world, tid, r, s);
-    idx = blocks[r].idx[s];
-    m = blocks[r].m[s];
-    u = blocks[r].unc[s];
-    sc = blocks[r].score[s];
+  // candidates c = tid + 256 j live in registers
+  long long idx[kPerThread];
+  double m[kPerThread], u[kPerThread], sc[kPerThread];
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    const int c = tid + kPlanThreads * j;
+    idx[j] = 0x7fffffffffffffffLL;
+    m[j] = 0.0;
+    u[j] = 0.0;
+    sc[j] = -INFINITY;
+    if (c < v.total) {
+      int r, q;
+      locate(v, world, c, r, q);
+      idx[j] = blocks[r].idx[q];
+      m[j] = blocks[r].m[q];
+      u[j] = blocks[r].unc[q];
+      sc[j] = blocks[r].score[q];
+    }
   }
-  const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kB, ctl->maxb)), remaining);
-  const int nwarps = (v.total + 31) >> 5;   // warps that hold candidates
   int nb = 0;
   for (int b = 0; b < maxpicks; ++b) {
-    // block arg-max: warp butterflies, one barrier, every warp reduces the warp winners again
-    Best me{sc, idx};
+    // block arg-max: thread-local, warp butterfly, ONE barrier, every warp reduces the 8 warp winners
+    Best me{sc[0], idx[0]};
     int pos = tid;
+#pragma unroll
+    for (int j = 1; j < kPerThread; ++j)
+      if (better(sc[j], idx[j], me.s, me.i)) {
+        me.s = sc[j];
+        me.i = idx[j];
+        pos = tid + kPlanThreads * j;
+      }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       const double s2 = __shfl_xor_sync(0xffffffffu, me.s, o);
@@ -1078,14 +1100,10 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
       s_pos[b & 1][warp] = pos;
     }
     __syncthreads();
-    Best win{-INFINITY, 0x7fffffffffffffffLL};
-    int wpos = 0;
-    if (lane < nwarps) {
-      win = s_b[b & 1][lane];
-      wpos = s_pos[b & 1][lane];
-    }
+    Best win = s_b[b & 1][lane & 7];
+    int wpos = s_pos[b & 1][lane & 7];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int o = 4; o; o >>= 1) {
       const double s2 = __shfl_xor_sync(0xffffffffu, win.s, o);
       const long long i2 = __shfl_xor_sync(0xffffffffu, win.i, o);
       const int p2 = __shfl_xor_sync(0xffffffffu, wpos, o);
@@ -1107,22 +1125,33 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
       out_idx[ctl->n_picked + nb] = win.i;
     }
     nb += 1;
-    if (tid < v.total) {
-      m = fmin(m, Dcc[(size_t)wpos * kCap + tid]);   // d is symmetric: the winner's row, coalesced
-      if (tid == wpos) u = 0.0;
-      sc = score_of(rule, wd, wu, m, u);
+    const double* __restrict__ drow = Dcc + (size_t)wpos * kCap;   // d is symmetric: the winner's row, coalesced
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int c = tid + kPlanThreads * j;
+      if (c < v.total) {
+        m[j] = fmin(m[j], drow[c]);
+        if (c == wpos) u[j] = 0.0;
+        sc[j] = score_of(rule, wd, wu, m[j], u[j]);
+      }
     }
   }
   // best surviving candidate score -> upper bound of every score after the pass
-  Best me{sc, idx};
+  Best me{sc[0], idx[0]};
+#pragma unroll
+  for (int j = 1; j < kPerThread; ++j)
+    if (better(sc[j], idx[j], me.s, me.i)) {
+      me.s = sc[j];
+      me.i = idx[j];
+    }
   me = warp_best(me);
   __syncthreads();
   if (lane == 0) s_b[0][warp] = me;
   __syncthreads();
   if (tid == 0) {
-    Best b = s_b[0][0];
-    for (int k = 1; k < 32; ++k)
-      if (better(s_b[0][k].s, s_b[0][k].i, b.s, b.i)) b = s_b[0][k];
+    Best bb = s_b[0][0];
+    for (int k = 1; k < 8; ++k)
+      if (better(s_b[0][k].s, s_b[0][k].i, bb.s, bb.i)) bb = s_b[0][k];
     long long inwin = 0;
     for (int r = 0; r < world; ++r) inwin += blocks[r].inwin;
     const double U = ctl->U;
@@ -1131,7 +1160,7 @@ __global__ void __launch_bounds__(kCap) plan_kernel(const RankBlock* blocks, Ran
     if (inwin < kTarget) W = fmin(U, W * 4.0);
     else if (frac < 1.0 / 16.0) W = W * 0.5;
     else if (frac > 0.5) W = fmin(U, W * 2.0);
-    ctl->U = fmax(b.s, v.theta);
+    ctl->U = fmax(bb.s, v.theta);
     ctl->W = W;
     ctl->nb = nb;          // nb >= 1: the first winner is the global argmax (score >= theta)
     ctl->n_picked += nb;
@@ -1456,7 +1485,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         }
         g_launches.fetch_add(1);
       }
-      plan_kernel<<<1, kCap, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
+      plan_kernel<<<1, kPlanThreads, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
       g_launches.fetch_add(1);
       PassArgs a{};
       fill_pass(a);

@@ -64,7 +64,7 @@ struct Ctl {
   double U, W;      // histogram window [U-W, U]; W <= 0: no window yet
   double theta_emit;   // the pass lists every owned row whose new score is >= theta_emit (+inf: none)
   int emit_mode, pad2; // RankBlock::mode of that list
-  unsigned int filter_ticket, pad0;
+  unsigned int filter_ticket, pairs_ticket;
   long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
 };
 
@@ -134,6 +134,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c[0]), "+d"(c[1])
       : "d"(a), "d"(b));
+}
+// volatile twin for the streaming kernels: keeps program order against the (volatile) ring loads,
+// so that the load of super-step s of the NEXT tile is issued right before the MMAs of step s of
+// this tile (a full tile of lead time) instead of wherever the scheduler lets it sink to
+__device__ __forceinline__ void dmma_v(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
 }
 
 // centers in shared memory: fp64, row stride S = dpad + 2 doubles (== 16 bytes mod 128, which
@@ -509,20 +517,89 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
   publish_pass(a, best, do_hist, s_hist);
 }
 
+// second half of the fast-path pass: one thread per row turns the kB canonical dot products
+// into the distance to the nearest new centre (min_j sqrt(max(t_j, 0)) == sqrt(max(min_j t_j, 0))
+// bit for bit, sqrt being monotone and correctly rounded: one square root per row instead of kB),
+// the running minimum, unc/score, the candidate list, the histogram and the arg-max
+struct ApplyConst {
+  double h_lo, h_inv, wd, wu, theta_emit;
+  int rule;
+  bool do_hist;
+};
+__device__ __forceinline__ ApplyConst apply_const(const PassArgs& a) {
+  ApplyConst c{0.0, 0.0, 0.0, 0.0, INFINITY, 0, false};
+  c.do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+  if (a.ctl) {
+    c.rule = a.ctl->rule;
+    c.wd = a.ctl->wd;
+    c.wu = a.ctl->wu;
+    c.theta_emit = a.ctl->theta_emit;
+    if (c.do_hist) {
+      c.h_lo = a.ctl->U - a.ctl->W;
+      c.h_inv = (double)kNB / a.ctl->W;
+    }
+  }
+  return c;
+}
+__device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c, long long i, const double* s_xxc,
+                                          const long long* s_pick, unsigned int* s_hist, Best& best) {
+  const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
+  const double xxi = a.xx[i];
+  double tm = INFINITY;
+  bool picked = false;
+#pragma unroll
+  for (int q = 0; q < kB / 2; ++q) {
+    const double2 d2 = __ldcg(dp + q);
+    tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
+    tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
+    picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
+  }
+  const double dmin = fmin(a.m[i], sqrt(fmax(tm, 0.0)));
+  a.m[i] = dmin;
+  if (a.unc) {
+    double u = a.unc[i];
+    if (picked) {
+      u = 0.0;  // uncertainty[ind] = 0  (:848)
+      a.unc[i] = 0.0;
+    }
+    const double sc = score_of(c.rule, c.wd, c.wu, dmin, u);
+    a.score[i] = sc;
+    if (a.send) emit_row(a.send, c.theta_emit, i, dmin, u, sc, best);
+    if (c.do_hist) {
+      const double fb = (sc - c.h_lo) * c.h_inv;
+      if (fb >= 0.0) {
+        const int hb = (int)fmin(fb, (double)(kNB - 1));
+        atomicAdd(&s_hist[hb], 1u);
+        atomicAdd(&s_hist[kNB], 1u);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the pass over X, fast path
-// d == 8 * 16 * STEPS (2048 for STEPS = 16).  Warp-specialised, one CTA per SM:
-//   * 8 COMPUTE warps = the 8 K-segments of one 8-row tile at a time.  Warp w keeps ITS 1/8 of
-//     the 8 centres in registers as fp64 B operands (STEPS x 4 doubles per lane), so the inner
-//     loop has no shared-memory traffic: per super-step one 16-byte global load (a STEPS-deep
-//     register ring keeps a whole tile per lane in flight), four fp32->fp64 converts, four
+// d == 8 * 16 * STEPS (2048 for STEPS = 16).  Warp-specialised, one CTA per SM, 8-row tiles:
+//   * PRODUCER (one warp): streams tiles into a ring of kStagesX shared-memory stages with 1-D TMA
+//     bulk copies (one 8 KB cp.async.bulk per row, completion counted on the stage's mbarrier) and
+//     refills a stage as soon as the 8 compute warps have released it, so two to three tiles
+//     (128-192 KB per SM) are always in flight no matter how the math is scheduled.
+//   * 8 COMPUTE warps = the 8 K-segments of a tile.  Warp w keeps ITS 1/8 of the 8 centres in
+//     registers as fp64 B operands (STEPS x 4 doubles per lane); per super-step it reads one
+//     float4 of A from the stage (row stride 8 KB + 64 B: conflict free), converts and issues four
 //     DMMAs.  A tile ends with one 16-byte shared store of the segment's partial dots and a
-//     non-blocking bar.arrive — compute warps never wait for anything but their own loads.
-//   * 4 EPILOGUE warps, one per partial buffer (tile k -> warp k mod 4, a pair of named barriers
+//     non-blocking bar.arrive.
+//   * 3 EPILOGUE warps, one per partial buffer (tile k -> warp k mod 3, a pair of named barriers
 //     per buffer): split-K reduction in the canonical order, 8x8 dot products to global memory
-//     (64 B per row, < 1 % of the traffic); apply_kernel finishes the rows.
-// setmaxnreg moves registers from the epilogue warpgroup (40) to the compute warpgroups (232): 8*32*232 + 4*32*40 = the 168*384 the CTA owns.
-constexpr int kPartBufs = 4;
-constexpr int kWsThreads = (kSeg + 4) * 32;   // 8 compute + 4 epilogue warps
+//     (64 B per row, < 1 % of the traffic).
+// After the tile loop the compute warps finish the CTA's own rows from those dot products
+// (apply_row) and the last CTA of the grid publishes the rank's block header.
+// setmaxnreg: compute warpgroups 216 registers, the producer/epilogue warpgroup 72.
+constexpr int kStagesX = 3;
+constexpr int kPartBufs = 3;
+constexpr int kRowBytesX = 2048 * 4 + 64;                  // stage row stride
+constexpr int kStageBytesX = 8 * kRowBytesX;               // 66 048
+constexpr int kWsThreads = (kSeg + 4) * 32;                // 8 compute warps + producer + 3 epilogue warps
+constexpr size_t kWsSmem = (size_t)kStagesX * kStageBytesX + sizeof(double) * kPartBufs * kSeg * 64 + 2 * kStagesX * 8 +
+                           kB * 16 + (kNB + 1) * 4 + 128;
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void named_sync(int id, int count) {
@@ -531,28 +608,54 @@ __device__ __forceinline__ void named_sync(int id, int count) {
 __device__ __forceinline__ void named_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
 
 template <int STEPS>
-__global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
-  __shared__ __align__(16) double s_part[kPartBufs][kSeg][64];   // [buf][segment][row*8 + centre]
+__global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
+  static_assert(STEPS * 16 * kSeg * 4 + 64 == kRowBytesX, "stage geometry is for d = 2048");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* stage0 = smem_raw;
+  double (*s_part)[kSeg][64] = reinterpret_cast<double (*)[kSeg][64]>(smem_raw + (size_t)kStagesX * kStageBytesX);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_part + kPartBufs);
+  uint64_t* empty = full + kStagesX;
+  double* s_xxc = reinterpret_cast<double*>(empty + kStagesX);
+  long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
+
   const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
   if (nb <= 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  if (threadIdx.x < kB) {
+    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];   // pad with the last centre: min() is idempotent
+    s_xxc[threadIdx.x] = a.xx[p];
+    s_pick[threadIdx.x] = p;
+  }
+  for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kStagesX; ++q) {
+      mbar_init(&full[q], 1);        // one expect_tx arrival + the bytes
+      mbar_init(&empty[q], kSeg);    // one arrival per compute warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   const long long ntiles = (a.hi - a.lo + 7) / 8;
   const int nt = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
   if (warp < kSeg) {
     // ------------------------------------------------------------------ compute warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int seg = warp, g = lane >> 2, kk = lane & 3;
-    const float4* X4 = reinterpret_cast<const float4*>(a.X);
-    const int lane_off = seg * (STEPS * 4) + kk;      // float4 offset of this lane inside a row
     double breg[STEPS][4];
     {
-      const long long pg = a.centers[min(g, nb - 1)];   // pad with the last centre: min() is idempotent
-      const float4* cp = X4 + (size_t)pg * a.d4 + lane_off;
+      const long long pg = a.centers[min(g, nb - 1)];
+      const float4* cp = reinterpret_cast<const float4*>(a.X) + (size_t)pg * a.d4 + seg * (STEPS * 4) + kk;
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
         const float4 v = __ldg(cp + 4 * s);
@@ -562,130 +665,86 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_ws(PassArgs a) {
         breg[s][3] = (double)v.w;
       }
     }
-    // this lane's rows are a.lo + g + 8 * (blockIdx.x + k * gridDim.x): a fixed stride apart.
-    // 32-bit float4 offsets from X (host checks n * d4 < 2^32) keep the loop state small: the
-    // 232 registers hold 128 of B operands, 64 of ring and 16 of accumulators.
-    unsigned ro = (unsigned)(min(a.lo + (long long)blockIdx.x * 8 + g, a.hi - 1) * a.d4 + lane_off);
-    const unsigned rstride = gridDim.x * 8u * (unsigned)a.d4;            // float4 between this lane's tiles
-    const unsigned rlast = (unsigned)((a.hi - 1) * a.d4 + lane_off);      // rows past the end re-read the last row
-    float4 ring[STEPS];
-    if (nt > 0) {
-#pragma unroll
-      for (int s = 0; s < STEPS; ++s) ring[s] = ldg_stream(X4 + ro + 4 * s);
-    }
+    const unsigned a_off = smem_addr(stage0) + g * kRowBytesX + seg * (STEPS * 64) + kk * 16;
     const unsigned my_part = smem_addr(&s_part[0][seg][lane * 2]);
+    int st = 0, pb = 0;
+    unsigned phase = 0;
     for (int k = 0; k < nt; ++k) {
-      const bool has_next = k + 1 < nt;
-      ro = min(ro + rstride, rlast);
-      const float4* np = X4 + ro;
+      mbar_wait(&full[st], phase);
+      const unsigned ap = a_off + st * kStageBytesX;
       double c[4][2];
 #pragma unroll
       for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
-        const float4 x = ring[s];
-        if (has_next) ring[s] = ldg_stream(np + 4 * s);
+        const float4 x = lds128(ap + s * 64);
         dmma(c[0], (double)x.x, breg[s][0]);
         dmma(c[1], (double)x.y, breg[s][1]);
         dmma(c[2], (double)x.z, breg[s][2]);
         dmma(c[3], (double)x.w, breg[s][3]);
       }
-      const int b = k & (kPartBufs - 1);
-      if (k >= kPartBufs) named_sync(1 + kPartBufs + b, kSeg * 32 + 32);   // buffer released by its epilogue warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);          // this warp has read its slice of the stage
+      if (++st == kStagesX) {
+        st = 0;
+        phase ^= 1u;
+      }
+      if (k >= kPartBufs) named_sync(1 + kPartBufs + pb, kSeg * 32 + 32);   // buffer released by its epilogue warp
       // lane (g,kk) holds (row g, centres 2kk, 2kk+1)
-      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_part + b * (unsigned)sizeof(s_part[0])),
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(my_part + pb * (unsigned)(sizeof(double) * kSeg * 64)),
                    "d"(combine4(c[0][0], c[1][0], c[2][0], c[3][0])), "d"(combine4(c[0][1], c[1][1], c[2][1], c[3][1]))
                    : "memory");
       asm volatile("fence.acq_rel.cta;" ::: "memory");   // partials visible before the arrive is counted
-      named_arrive(1 + b, kSeg * 32 + 32);
+      named_arrive(1 + pb, kSeg * 32 + 32);
+      if (++pb == kPartBufs) pb = 0;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    // epilogue warp ew owns partial buffer ew, i.e. tiles k = ew, ew+4, ...: it finishes the split-K
-    // sums in the canonical order and stores the 8x8 dot products of the tile (apply_kernel turns
-    // them into distances / scores).  Deliberately tiny: this warpgroup lives in 40 registers and
-    // anything it spilled would queue in front of the compute warps' global loads.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    const int ew = warp - kSeg;
-    const int r = lane >> 2;                    // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
-    for (int k = ew; k < nt; k += kPartBufs) {
-      named_sync(1 + ew, kSeg * 32 + 32);
-      const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
-      const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
-      if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
-      const long long row = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + r;   // relative to a.lo
-      if (a.lo + row < a.hi) *reinterpret_cast<double2*>(a.dots + row * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
-    }
-  }
-}
-
-// second half of the fast-path pass: one thread per owned row turns the kB dot products into
-// distances, the running minimum, unc/score, the candidate list, the histogram and the arg-max
-__global__ void __launch_bounds__(256) apply_kernel(PassArgs a) {
-  __shared__ double s_xxc[kB];
-  __shared__ long long s_pick[kB];
-  __shared__ unsigned int s_hist[kNB + 1];
-  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
-  if (nb <= 0) return;
-  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
-  if (threadIdx.x < kB) {
-    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];
-    s_xxc[threadIdx.x] = a.xx[p];
-    s_pick[threadIdx.x] = p;
-  }
-  if (do_hist)
-    for (int b = threadIdx.x; b < kNB + 1; b += blockDim.x) s_hist[b] = 0u;
-  double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0, theta_emit = INFINITY;
-  int rule = 0;
-  if (a.ctl) {
-    rule = a.ctl->rule;
-    wd = a.ctl->wd;
-    wu = a.ctl->wu;
-    theta_emit = a.ctl->theta_emit;
-    if (do_hist) {
-      h_lo = a.ctl->U - a.ctl->W;
-      h_inv = (double)kNB / a.ctl->W;
-    }
-  }
-  __syncthreads();
-  Best best{-INFINITY, 0x7fffffffffffffffLL};
-  for (long long i = a.lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi; i += (long long)gridDim.x * blockDim.x) {
-    const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
-    const double xxi = a.xx[i];
-    // min_j sqrt(max(t_j, 0)) == sqrt(max(min_j t_j, 0)) bit for bit (sqrt is monotone and correctly
-    // rounded), so one square root per row instead of kB
-    double tm = INFINITY;
-    bool picked = false;
-#pragma unroll
-    for (int q = 0; q < kB / 2; ++q) {
-      const double2 d2 = dp[q];
-      tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
-      tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
-      picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
-    }
-    const double dmin = fmin(a.m[i], sqrt(fmax(tm, 0.0)));
-    a.m[i] = dmin;
-    if (a.unc) {
-      double u = a.unc[i];
-      if (picked) {
-        u = 0.0;  // uncertainty[ind] = 0  (:848)
-        a.unc[i] = 0.0;
-      }
-      const double sc = score_of(rule, wd, wu, dmin, u);
-      a.score[i] = sc;
-      if (a.send) emit_row(a.send, theta_emit, i, dmin, u, sc, best);
-      if (do_hist) {
-        const double fb = (sc - h_lo) * h_inv;
-        if (fb >= 0.0) {
-          const int hb = (int)fmin(fb, (double)(kNB - 1));
-          atomicAdd(&s_hist[hb], 1u);
-          atomicAdd(&s_hist[kNB], 1u);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == kSeg) {
+      // ---------------------------------------------------------------- producer warp
+      // lane r < 8 copies row r of every tile; rows past the end re-read the last row
+      int st = 0;
+      unsigned phase = 0;
+      for (int k = 0; k < nt; ++k) {
+        if (k >= kStagesX) mbar_wait(&empty[st], phase ^ 1u);   // the stage's previous tile was released
+        if (lane == 0) mbar_expect_tx(&full[st], 8u * 2048u * 4u);
+        __syncwarp();
+        if (lane < 8) {
+          const long long row = min(a.lo + ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + lane, a.hi - 1);
+          tma_load_1d(stage0 + (size_t)st * kStageBytesX + lane * kRowBytesX, a.X + (size_t)row * 2048, 2048u * 4u, &full[st]);
+        }
+        if (++st == kStagesX) {
+          st = 0;
+          phase ^= 1u;
         }
       }
+    } else {
+      // ---------------------------------------------------------------- epilogue warps
+      const int ew = warp - kSeg - 1;             // partial buffer of this warp: tiles k = ew, ew+3, ...
+      const int r = lane >> 2;                    // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
+      for (int k = ew; k < nt; k += kPartBufs) {
+        named_sync(1 + ew, kSeg * 32 + 32);
+        const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
+        const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
+        if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
+        const long long row = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + r;   // relative to a.lo
+        if (a.lo + row < a.hi) *reinterpret_cast<double2*>(a.dots + row * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
+      }
+    }
+  }
+  // ---- apply phase: the CTA's own rows (their dot products were written by its own epilogue
+  // warps, visible after the barrier), one row per compute-warpgroup thread at a time
+  __syncthreads();
+  Best best{-INFINITY, 0x7fffffffffffffffLL};
+  const ApplyConst ac = apply_const(a);
+  if (warp < kSeg) {
+    for (int q = threadIdx.x; q < nt * 8; q += kSeg * 32) {
+      const long long i = a.lo + ((long long)blockIdx.x + (long long)(q >> 3) * gridDim.x) * 8 + (q & 7);
+      if (i < a.hi) apply_row(a, ac, i, s_xxc, s_pick, s_hist, best);
     }
   }
   __syncthreads();
-  publish_pass(a, best, do_hist, s_hist);
+  publish_pass(a, best, ac.do_hist, s_hist);
 }
 
 static size_t pass_smem_bytes(int S) {
@@ -832,23 +891,14 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
   }
 }
 
-// fast path (d == 8 * 16 * STEPS): the pass kernel's tile machine on the gathered candidates.
-// CTA (cb, y): the 8 candidates of column block cb are the centres (their 1/8 K-slices live in the
-// registers of the 8 warps), row tiles y, y + gridDim.y, ... of the candidate list stream through
-// a register ring (from L2 mostly: the rows were just touched by the pass).  After the split-K
-// exchange warp w finishes row w of the tile: lane j writes d(row, centre j).
+__device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double* Dcc, unsigned int* hist,
+                          long long* out_idx, Ctl* ctl);
+
 template <int STEPS>
-__global__ void __launch_bounds__(kSeg * 32, 1) pairs_kernel_reg(const float* __restrict__ X, int d4,
-                                                                 const double* __restrict__ xx, const RankBlock* blocks,
-                                                                 const Ctl* ctl, double* __restrict__ Dcc) {
-  if (ctl->n_picked >= ctl->k) return;
-  __shared__ __align__(16) double s_part[2][kSeg][64];
-  __shared__ double s_xxc[kB];
-  const int world = ctl->world;
-  const CandView v = view_of(blocks, world);
-  if (v.fallback) return;
+__device__ __forceinline__ void pairs_tiles(const float* __restrict__ X, int d4, const double* __restrict__ xx,
+                                            const RankBlock* blocks, const CandView& v, int world,
+                                            double* __restrict__ Dcc, double (*s_part)[kSeg][64], double* s_xxc) {
   const int col0 = blockIdx.x * kB;
-  if (col0 >= v.total) return;
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
   const float4* X4 = reinterpret_cast<const float4*>(X);
   const int lane_off = seg * (STEPS * 4) + kk;
@@ -905,6 +955,44 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_kernel_reg(const float* __
       Dcc[(size_t)myrow * kCap + col0 + lane] = dist_from_dot(dot, xxi, s_xxc[lane]);
     }
     buf ^= 1;
+  }
+}
+
+// fast path (d == 8 * 16 * STEPS): the pass kernel's tile machine on the gathered candidates.
+// CTA (cb, y): the 8 candidates of column block cb are the centres (their 1/8 K-slices live in the
+// registers of the 8 warps), row tiles y, y + gridDim.y, ... of the candidate list stream through
+// a register ring (from L2 mostly: the rows were just touched by the pass).  After the split-K
+// exchange warp w finishes row w of the tile: lane j writes d(row, centre j).
+// The last CTA of the grid to finish runs the planner (plan_body) on the completed matrix, so a
+// round needs no separate plan launch.
+template <int STEPS>
+__global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* __restrict__ X, int d4,
+                                                                  const double* __restrict__ xx, const RankBlock* blocks,
+                                                                  RankBlock* send, unsigned int* hist, long long* out_idx,
+                                                                  Ctl* ctl, double* __restrict__ Dcc) {
+  __shared__ __align__(16) double s_part[2][kSeg][64];
+  __shared__ double s_xxc[kB];
+  __shared__ unsigned int s_last;
+  if (ctl->n_picked >= ctl->k) {       // (uniform over the grid: nobody takes a ticket)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctl->nb = 0;
+    return;
+  }
+  {
+    const int world = ctl->world;
+    const CandView v = view_of(blocks, world);
+    if (!v.fallback && (int)blockIdx.x * kB < v.total) pairs_tiles<STEPS>(X, d4, xx, blocks, v, world, Dcc, s_part, s_xxc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y;
+    s_last = (atomicAdd(&ctl->pairs_ticket, 1u) == total - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x == 0) ctl->pairs_ticket = 0;
+    plan_body(blocks, send, Dcc, hist, out_idx, ctl);
   }
 }
 
@@ -1012,9 +1100,8 @@ __device__ void choose_theta(const unsigned int* __restrict__ hist, double U, do
 constexpr int kPlanThreads = 256;
 constexpr int kPerThread = kCap / kPlanThreads;   // candidates per planner thread (strided: c = tid + 256 j)
 
-__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blocks, RankBlock* send,
-                                                            const double* __restrict__ Dcc, unsigned int* hist,
-                                                            long long* __restrict__ out_idx, Ctl* ctl) {
+__device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double* Dcc, unsigned int* hist,
+                          long long* out_idx, Ctl* ctl) {
   __shared__ Best s_b[2][8];
   __shared__ int s_pos[2][8];
   __shared__ double s_theta;
@@ -1125,12 +1212,12 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blo
       out_idx[ctl->n_picked + nb] = win.i;
     }
     nb += 1;
-    const double* __restrict__ drow = Dcc + (size_t)wpos * kCap;   // d is symmetric: the winner's row, coalesced
+    const double* drow = Dcc + (size_t)wpos * kCap;   // d is symmetric: the winner's row, coalesced
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
       const int c = tid + kPlanThreads * j;
       if (c < v.total) {
-        m[j] = fmin(m[j], drow[c]);
+        m[j] = fmin(m[j], __ldcg(drow + c));
         if (c == wpos) u[j] = 0.0;
         sc[j] = score_of(rule, wd, wu, m[j], u[j]);
       }
@@ -1169,6 +1256,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blo
     ctl->first_round = 0;
     send->count = 0;
   }
+}
+
+__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blocks, RankBlock* send, const double* Dcc,
+                                                            unsigned int* hist, long long* out_idx, Ctl* ctl) {
+  plan_body(blocks, send, Dcc, hist, out_idx, ctl);
 }
 
 // distances of every row to a list of centers, for the parity tests
@@ -1324,21 +1416,16 @@ static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullp
   if (!configured) {
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
     configured = true;
   }
   if (ev0) cudaEventRecord(ev0, stream);
-  const bool fast = a.d4 == kSeg * 4 * 16 && a.dots != nullptr && (unsigned long long)a.n * a.d4 < (1ULL << 32);   // d = 2048
-  if (fast) pass_kernel_ws<16><<<sm_count(), kWsThreads, 0, stream>>>(a);
+  const bool fast = a.d4 == kSeg * 4 * 16 && a.dots != nullptr;   // d = 2048
+  if (fast) pass_kernel_tma<16><<<sm_count(), kWsThreads, kWsSmem, stream>>>(a);
   else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   if (ev1) cudaEventRecord(ev1, stream);
   VQ_LAUNCHED();
-  if (fast) {
-    const long long rows = a.hi - a.lo;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 255) / 256, (long long)sm_count() * 8));
-    apply_kernel<<<grid, 256, 0, stream>>>(a);
-    VQ_LAUNCHED();
-  }
   return 0;
 }
 
@@ -1476,17 +1563,15 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         }
       }
       if (nbk > 1) {
-        if (fast_d) {
-          dim3 pg(kCap / kB, 4);
-          pairs_kernel_reg<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, recv, ctl, Dcc);
-        } else {
-          dim3 pg(kCap / kB, 4);
-          pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
-        }
+        dim3 pg(kCap / kB, 4);
+        if (fast_d) pairs_plan_kernel<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, recv, send, hist, (long long*)out_idx, ctl, Dcc);
+        else pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
         g_launches.fetch_add(1);
       }
-      plan_kernel<<<1, kPlanThreads, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
-      g_launches.fetch_add(1);
+      if (nbk == 1 || !fast_d) {
+        plan_kernel<<<1, kPlanThreads, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
+        g_launches.fetch_add(1);
+      }
       PassArgs a{};
       fill_pass(a);
       const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();

@@ -125,7 +125,9 @@ def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_loca
     mine = lab[(lab >= lo) & (lab < hi)] - lo
     if mine.size:
         unl[torch.from_numpy(mine).to(dev)] = 0
-    unc_local = qp.fuse(unl, thc_vs_wpu, labeled_ratio=lab.size / max(n, 1), group=group if world > 1 else None,
+    # (group=None means the default group to torch.distributed but "single GPU" to QueryPass.fuse)
+    fuse_group = (group if group is not None else td.group.WORLD) if world > 1 else None
+    unc_local = qp.fuse(unl, thc_vs_wpu, labeled_ratio=lab.size / max(n, 1), group=fuse_group,
                         n_unlabeled_global=n - lab.size)
     X = allgather_rows(X_local, n, world, group)
     unc = allgather_rows(unc_local, n, world, group)

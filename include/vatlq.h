@@ -131,8 +131,9 @@ int vatlq_fuse_final(const uint8_t* unlabeled, int64_t n, const double* stats2,
  *         1 fixed       argmax(min_d + lambda*unc)                   (:822-827)
  *         2 dist        argmax(min_d); first pick given by caller    (:828-833)
  *   n_labeled == 0: the first pick is argmax(unc) (rule 0/1) or `first_pick` (rule 2).
- *   batch: 1 = one pick per pass over X (GEMV form); >1 = up to `batch` picks per pass,
- *          decided exactly in advance on a candidate set.
+ *   batch: 1 = one pick per round (GEMV form: plain arg-max, one pass over X per pick);
+ *          >1 = up to `batch` (<= 16) picks per round, decided exactly in advance on a candidate
+ *          set and applied 8 per pass over X.
  * out_idx[k] int64 picks in order (device).  min_d[n] fp64 in/out (initialised by
  * vatlq_coreset_init), unc[n] fp64 in/out (picked entries zeroed like :848).
  * host_stats (optional, 8 x int64, host memory, written at the end — the call then

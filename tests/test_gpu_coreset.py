@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("batch", [1, 8])
+@pytest.mark.parametrize("batch", [1, 8, 16])
 def test_golden_coreset(built_lib, gold_coreset, batch):
     v = built_lib
     for tag, c in gold_coreset.items():

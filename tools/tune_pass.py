@@ -10,15 +10,16 @@ from vatlq import ops, synth
 
 lib = vatlq._lib.lib()
 dev = "cuda:0"
+BATCH = int(os.environ.get("BATCH", 8))
 for rows, k in ((170000, 800), (21250, 800)):  # run under `timeout -s KILL`
     X = synth.device_embeddings(rows, dev, seed=2)
     unc = torch.rand(rows, dtype=torch.float64, device=dev)
-    ops.coreset_select(X, unc, [], 16, 0.6, 0.01, batch=8)
+    ops.coreset_select(X, unc, [], 16, 0.6, 0.01, batch=BATCH)
     lib.vatlq_profile_passes(1)
     lib.vatlq_profile_read(None, None, None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    picks, st = ops.coreset_select(X, unc, [], k, 0.6, 0.01, batch=8)
+    picks, st = ops.coreset_select(X, unc, [], k, 0.6, 0.01, batch=BATCH)
     e1.record()
     torch.cuda.synchronize()
     ms, n, p = C.c_double(), C.c_int64(), C.c_int64()

@@ -27,7 +27,8 @@
 
 namespace vatlq {
 
-constexpr int kB = 8;        // picks applied per pass over X
+constexpr int kB = 8;        // centres applied per pass over X (the DMMA tile width)
+constexpr int kMaxPicks = 16; // picks planned per round: applied by kMaxPicks / kB passes back to back
 #ifndef VQ_PASS_THREADS
 #define VQ_PASS_THREADS 512
 #endif
@@ -55,8 +56,8 @@ struct RankBlock {  // the all-gather unit: one per rank per round
 
 struct Ctl {
   long long n_picked, k;
-  long long picks[kB];
-  int nb;           // picks the next pass applies
+  long long picks[kMaxPicks];
+  int nb;           // picks this round applies (pass p takes picks[8p .. 8p+7])
   int first_round;  // labelled set empty: score = unc, exactly one pick (ActiveLearning.py:816-818)
   int rule, world;
   int maxb, pad1;   // picks per pass allowed (1 = GEMV form: plain argmax every round)
@@ -261,14 +262,24 @@ struct PassArgs {
   double* unc;               // null: distance-only pass (labelled-set initialisation)
   double* score;
   const long long* centers;  // device list of centers to apply
-  const int* n_centers;      // device count (<= kB), or null -> n_centers_imm
+  const int* n_centers;      // device count of the whole list, or null -> n_centers_imm
   int n_centers_imm;
+  int center_off;            // this pass applies centers[center_off .. center_off + kB); the pass that
+                             // reaches the end of the list is the one that emits / publishes
   Ctl* ctl;                  // null for initialisation passes
   unsigned int* hist;        // null: no histogram
   RankBlock* send;           // null: do not list candidates / arg-max (initialisation passes)
   Best* partial;             // per-CTA arg-max scratch (gridDim entries)
+  unsigned char* did_work;   // optional: set to 1 when this launch applied centres (pass timing bookkeeping)
   double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
 };
+
+// centres of THIS pass: count (<= 0: nothing to do) and whether it is the round's last pass
+__device__ __forceinline__ int pass_centers(const PassArgs& a, bool& final_pass) {
+  const int total = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  final_pass = a.center_off + kB >= total;
+  return min(kB, total - a.center_off);
+}
 
 // ---- what the epilogue of a pass leaves behind for the next round -------------------------
 // every owned row: running arg-max of the new scores; rows with score >= theta_emit are listed
@@ -291,7 +302,7 @@ __device__ __forceinline__ void emit_row(RankBlock* send, double theta_emit, lon
 
 // flush the CTA's histogram, reduce the arg-max over the CTA, and let the last CTA of the grid
 // finish the rank's block header (every thread of the CTA calls this)
-__device__ void publish_pass(const PassArgs& a, Best best, bool do_hist, const unsigned int* s_hist) {
+__device__ void publish_pass(const PassArgs& a, Best best, bool do_hist, const unsigned int* s_hist, bool final_pass) {
   __shared__ Best s_best[32];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x, nw = (blockDim.x + 31) >> 5;
@@ -299,7 +310,7 @@ __device__ void publish_pass(const PassArgs& a, Best best, bool do_hist, const u
     for (int b = tid; b < kNB + 1; b += blockDim.x)
       if (s_hist[b]) atomicAdd(&a.hist[b], s_hist[b]);
   }
-  if (a.send == nullptr) return;
+  if (a.send == nullptr || !final_pass) return;
   best = warp_best(best);
   if ((tid & 31) == 0) s_best[tid >> 5] = best;
   __syncthreads();
@@ -342,8 +353,10 @@ constexpr int kTeams = kPassThreads / 32 / kSeg;   // 2 teams of 8 warps
 template <bool GUARD>
 __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  bool final_pass;
+  const int nb = pass_centers(a, final_pass);
   if (nb <= 0) return;
+  const long long* centers = a.centers + a.center_off;
   double* s_c = reinterpret_cast<double*>(smem_raw);
   double* s_xxc = s_c + (size_t)kB * a.S;
   double* s_part = s_xxc + kB;                               // [team][buf][seg][64]
@@ -352,16 +365,19 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
   const int team = warp / kSeg, seg = warp % kSeg;
   const int dpad = a.nss * 16;
-  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.ctl) a.ctl->stat_passes += 1;
+    if (a.did_work) *a.did_work = 1;
+  }
   for (int j = 0; j < kB; ++j) {
-    const long long p = a.centers[min(j, nb - 1)];  // pad with the last center: min() is idempotent
+    const long long p = centers[min(j, nb - 1)];  // pad with the last center: min() is idempotent
     stage_center(a.X, a.d4, dpad, a.S, p, j, s_c);
     if (threadIdx.x == 0) {
       s_xxc[j] = a.xx[p];
       s_pick[j] = p;
     }
   }
-  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+  const bool do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0 && final_pass;
   double h_lo = 0.0, h_inv = 0.0, wd = 0.0, wu = 0.0, theta_emit = INFINITY;
   int rule = 0;
   Best best{-INFINITY, 0x7fffffffffffffffLL};
@@ -423,7 +439,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
           }
           const double sc = score_of(rule, wd, wu, dmin, u);
           a.score[i] = sc;
-          if (a.send) emit_row(a.send, theta_emit, i, dmin, u, sc, best);
+          if (a.send && final_pass) emit_row(a.send, theta_emit, i, dmin, u, sc, best);
           if (do_hist) {
             const double fb = (sc - h_lo) * h_inv;
             if (fb >= 0.0) {
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
     }
   }
   __syncthreads();
-  publish_pass(a, best, do_hist, s_hist);
+  publish_pass(a, best, do_hist, s_hist, final_pass);
 }
 
 // second half of the fast-path pass: one thread per row turns the kB canonical dot products
@@ -524,11 +540,12 @@ __global__ void __launch_bounds__(kPassThreads, 1) pass_kernel_generic(PassArgs 
 struct ApplyConst {
   double h_lo, h_inv, wd, wu, theta_emit;
   int rule;
-  bool do_hist;
+  bool do_hist, emit;
 };
-__device__ __forceinline__ ApplyConst apply_const(const PassArgs& a) {
-  ApplyConst c{0.0, 0.0, 0.0, 0.0, INFINITY, 0, false};
-  c.do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0;
+__device__ __forceinline__ ApplyConst apply_const(const PassArgs& a, bool final_pass) {
+  ApplyConst c{0.0, 0.0, 0.0, 0.0, INFINITY, 0, false, false};
+  c.do_hist = a.hist != nullptr && a.ctl != nullptr && a.ctl->W > 0.0 && final_pass;
+  c.emit = a.send != nullptr && final_pass;
   if (a.ctl) {
     c.rule = a.ctl->rule;
     c.wd = a.ctl->wd;
@@ -564,7 +581,7 @@ __device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c
     }
     const double sc = score_of(c.rule, c.wd, c.wu, dmin, u);
     a.score[i] = sc;
-    if (a.send) emit_row(a.send, c.theta_emit, i, dmin, u, sc, best);
+    if (c.emit) emit_row(a.send, c.theta_emit, i, dmin, u, sc, best);
     if (c.do_hist) {
       const double fb = (sc - c.h_lo) * c.h_inv;
       if (fb >= 0.0) {
@@ -626,12 +643,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
   unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
 
-  const int nb = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  bool final_pass;
+  const int nb = pass_centers(a, final_pass);
   if (nb <= 0) return;
+  const long long* centers = a.centers + a.center_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (a.ctl && blockIdx.x == 0 && threadIdx.x == 0) a.ctl->stat_passes += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.ctl) a.ctl->stat_passes += 1;
+    if (a.did_work) *a.did_work = 1;
+  }
   if (threadIdx.x < kB) {
-    const long long p = a.centers[min((int)threadIdx.x, nb - 1)];   // pad with the last centre: min() is idempotent
+    const long long p = centers[min((int)threadIdx.x, nb - 1)];   // pad with the last centre: min() is idempotent
     s_xxc[threadIdx.x] = a.xx[p];
     s_pick[threadIdx.x] = p;
   }
@@ -654,7 +676,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     const int seg = warp, g = lane >> 2, kk = lane & 3;
     double breg[STEPS][4];
     {
-      const long long pg = a.centers[min(g, nb - 1)];
+      const long long pg = centers[min(g, nb - 1)];
       const float4* cp = reinterpret_cast<const float4*>(a.X) + (size_t)pg * a.d4 + seg * (STEPS * 4) + kk;
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
@@ -736,7 +758,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   // warps, visible after the barrier), one row per compute-warpgroup thread at a time
   __syncthreads();
   Best best{-INFINITY, 0x7fffffffffffffffLL};
-  const ApplyConst ac = apply_const(a);
+  const ApplyConst ac = apply_const(a, final_pass);
   if (warp < kSeg) {
     for (int q = threadIdx.x; q < nt * 8; q += kSeg * 32) {
       const long long i = a.lo + ((long long)blockIdx.x + (long long)(q >> 3) * gridDim.x) * 8 + (q & 7);
@@ -744,7 +766,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     }
   }
   __syncthreads();
-  publish_pass(a, best, ac.do_hist, s_hist);
+  publish_pass(a, best, ac.do_hist, s_hist, final_pass);
 }
 
 static size_t pass_smem_bytes(int S) {
@@ -1134,7 +1156,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
   const int rule = ctl->rule;
   const double wd = ctl->wd, wu = ctl->wu;
   const long long remaining = ctl->k - ctl->n_picked;
-  const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kB, ctl->maxb)), remaining);
+  const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kMaxPicks, ctl->maxb)), remaining);
   __syncthreads();   // every thread has read the block headers / ctl before thread 0 may change them
   if (v.fallback) {
     if (tid == 0) fallback_pick(blocks, world, v.fallback, send, out_idx, ctl);
@@ -1335,7 +1357,7 @@ struct Comm {
 
 // ---------------------------------------------------------------- workspace layout
 struct WsLayout {
-  size_t xx, score, hist, partial, send, recv, dcc, ctl, dots, total;
+  size_t xx, score, hist, partial, send, recv, dcc, ctl, dots, flags, total;
 };
 static WsLayout ws_layout(long long n, int world) {
   WsLayout L;
@@ -1354,6 +1376,7 @@ static WsLayout ws_layout(long long n, int world) {
   L.recv = take(sizeof(RankBlock) * (size_t)kMaxRanks);
   L.dcc = take((size_t)kCap * kCap * 8);
   L.dots = take((size_t)n * kB * 8);
+  L.flags = take(1024);
   L.total = o;
   return L;
 }
@@ -1482,9 +1505,10 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   RankBlock* send = (RankBlock*)(w + L.send);
   RankBlock* recv = (world > 1) ? (RankBlock*)(w + L.recv) : send;
   double* Dcc = (double*)(w + L.dcc);
+  unsigned char* flags = (unsigned char*)(w + L.flags);
   const Geom G = geom_of(d);
-  int nbk = 1;   // picks per pass: the power of two <= min(batch, kB)
-  while (nbk * 2 <= kB && nbk * 2 <= batch) nbk *= 2;
+  int nbk = 1;   // picks per round: the power of two <= min(batch, kMaxPicks)
+  while (nbk * 2 <= kMaxPicks && nbk * 2 <= batch) nbk *= 2;
 
   Ctl h{};
   h.n_picked = 0; h.k = k; h.nb = 0; h.rule = rule; h.world = world;
@@ -1553,6 +1577,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     double per_round = (rounds_done > 8 && picked > 0) ? (double)picked / (double)rounds_done : (double)std::max(1, nbk / 2);
     long long chunk = (long long)((double)remaining / std::max(1.0, per_round)) + 2;
     chunk = std::max<long long>(4, std::min<long long>(chunk, 256));
+    if (g_prof.on) VQ_CUDA(cudaMemsetAsync(flags, 0, 1024, stream));
     for (long long it = 0; it < chunk && rc == 0; ++it) {
       if (world > 1) {
         const int e = g_nccl.AllGather(send, recv, sizeof(RankBlock), /*ncclChar*/ 0, comm->nccl, stream);
@@ -1572,11 +1597,15 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         plan_kernel<<<1, kPlanThreads, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
         g_launches.fetch_add(1);
       }
-      PassArgs a{};
-      fill_pass(a);
-      const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
-      rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
-      if (timed) g_prof.used += 2;
+      for (int off = 0; off < nbk && rc == 0; off += kB) {   // picks [off, off+8) of the round; the last pass emits
+        PassArgs a{};
+        fill_pass(a);
+        a.center_off = off;
+        const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
+        if (timed) a.did_work = flags + g_prof.used / 2;
+        rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
+        if (timed) g_prof.used += 2;
+      }
     }
     if (rc) break;
     rounds_done += chunk;
@@ -1590,14 +1619,16 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     }
     const Ctl* hc = (const Ctl*)h_picked;
     if (g_prof.on) {
-      // only the first (stat_passes - passes_seen) launches of this chunk did work; later ones
-      // found nb == 0 (all picks made) and returned at once
-      const long long real = std::min<long long>(hc->stat_passes - passes_seen, (long long)(g_prof.used / 2));
-      for (long long i = 0; i < real; ++i) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
-          g_prof.total_ms += ms;
-          g_prof.timed += 1;
+      // launches of surplus rounds / of a round's unused second pass return at once: only the
+      // launches that flagged work are timed
+      unsigned char h_flags[1024];
+      if (cudaMemcpy(h_flags, flags, 1024, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        for (size_t i = 0; i < g_prof.used / 2; ++i) {
+          float ms = 0.f;
+          if (h_flags[i] && cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
+            g_prof.total_ms += ms;
+            g_prof.timed += 1;
+          }
         }
       }
       g_prof.picks += hc->n_picked - picked;

@@ -259,7 +259,7 @@ def main():
         picks_per_launch = n_picks.value / n_pass.value
         avg_s = tot_ms.value / n_pass.value * 1e-3
         achieved = per_pass_bytes / avg_s / 1e9
-        roof = {"kernel": "pass_kernel (core-set distance update on fp64 tensor cores, DMMA)", "bound": "hbm",
+        roof = {"kernel": "pass_kernel_tma (core-set distance update: TMA-staged tiles, fp64 tensor-core DMMA, row finishing)", "bound": "hbm",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": ncu_traffic("pass_kernel", nl),
                 "peak_source": peak_src, "avg_launch_us": avg_s * 1e6, "launches_timed": n_pass.value,

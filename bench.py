@@ -45,8 +45,11 @@ def parse():
     p.add_argument("--query-frac", type=float, default=0.05)
     p.add_argument("--labeled-frac", type=float, default=0.0, help="already-labelled fraction (0 = round 0)")
     p.add_argument("--moks", type=float, default=None, help="mean OKS of the last queries (default 0 at round 0, else 0.6)")
-    p.add_argument("--batch", type=int, default=8, help="core-set picks per pass over X (1 = GEMV form)")
+    p.add_argument("--batch", type=int, default=None,
+                   help="core-set picks per round (1 = GEMV form, 8 = one pass per round, 16 = two passes per round); "
+                        "default 8, and 16 from 4 GPUs on where the fixed cost of a round outweighs the pass")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather per round instead of the peer-memory mailbox")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-frames", type=int, default=512, help="frames of the CPU scoring sample")
     p.add_argument("--cpu-greedy-steps", type=int, default=6, help="greedy steps of the CPU core-set sample")
@@ -146,6 +149,8 @@ def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if a.batch is None:
+        a.batch = 16 if world >= 4 else 8
     local = int(os.environ.get("LOCAL_RANK", 0))
     n = a.frames
     n_lab = int(n * a.labeled_frac)
@@ -156,6 +161,7 @@ def main():
                 f"select {k} ({a.query_frac:.0%}), labelled {n_lab}, moks {moks}")
     config = {"workload": workload, "frames": n, "k": k, "feat_dim": D, "labelled": n_lab, "moks": moks,
               "unc_lambda": lam, "coreset_batch": a.batch, "parallelism": f"frame-range sharding x{world}",
+              "candidate_exchange": "none" if world == 1 else ("ncclAllGather" if a.no_p2p else "peer-memory mailbox (NVLink stores + flags)"),
               "l2": "inputs (>= 4 GB of heat maps + >= 174 MB of features per rank) exceed the 126 MB L2"}
 
     if a.impl == "reference":
@@ -203,7 +209,7 @@ def main():
     W = synth.ae_weights(42, 4)
     gcpu = torch.Generator().manual_seed(5)
     labeled = torch.randperm(n, generator=gcpu)[:n_lab].tolist() if n_lab else []
-    comm = vd.Comm() if world > 1 else None
+    comm = vd.Comm(use_p2p=not a.no_p2p) if world > 1 else None
     lib = vatlq._lib.lib()
     lib.vatlq_profile_passes(1)
 

@@ -168,6 +168,12 @@ int vatlq_profile_read(double* host_total_ms, int64_t* host_launches, int64_t* h
  * ------------------------------------------------------------------------------------ */
 int vatlq_comm_unique_id(void* host_id128);                 /* rank 0: 128-byte id       */
 int vatlq_comm_init(const void* host_id128, int rank, int world, void** comm_out);
+/* Optional peer-memory candidate exchange (replaces the per-round ncclAllGather with NVLink peer
+ * stores + flags issued by the kernels themselves): every rank calls _mailbox_handle (64-byte
+ * cudaIpcMemHandle_t of its mailbox), the handles are exchanged out of band (rank order) and
+ * every rank calls _attach with all of them.  Without _attach the NCCL path is used. */
+int vatlq_comm_mailbox_handle(void* comm, void* host_handle64);
+int vatlq_comm_attach(void* comm, const void* host_handles /* world x 64 bytes */, int world);
 int vatlq_comm_destroy(void* comm);
 
 #ifdef __cplusplus

@@ -19,7 +19,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     td.init_process_group("nccl", device_id=dev)
-    comm = vd.Comm()
+    comm = vd.Comm(use_p2p=os.environ.get("VATLQ_NO_P2P") is None)
+    if rank == 0:
+        print("candidate exchange:", "peer-memory mailbox" if comm.p2p else "ncclAllGather", flush=True)
     ok = True
     for n, k, d, n_lab, moks in ((1501, 97, 2048, 0, 0.0), (4003, 160, 2048, 300, 0.6), (777, 40, 256, 50, 0.6)):
         rng = np.random.default_rng(n)

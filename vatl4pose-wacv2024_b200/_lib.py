@@ -33,6 +33,8 @@ SIGNATURES = {
     "vatlq_profile_read": (_int, [_vp, _vp, _vp, _int]),
     "vatlq_comm_unique_id": (_int, [_vp]),
     "vatlq_comm_init": (_int, [_vp, _int, _int, C.POINTER(_vp)]),
+    "vatlq_comm_mailbox_handle": (_int, [_vp, _vp]),
+    "vatlq_comm_attach": (_int, [_vp, _vp, _int]),
     "vatlq_comm_destroy": (_int, [_vp]),
 }
 

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <vector>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -36,7 +37,7 @@ constexpr int kPassThreads = VQ_PASS_THREADS;
 constexpr int kCapL = 1024;  // candidate records per rank
 constexpr int kCap = 1024;   // candidates the planner handles (one per thread)
 constexpr int kNB = 1024;    // score-histogram bins
-constexpr int kTarget = 256; // wanted candidates per round (all ranks together)
+constexpr int kTarget = 256; // default wanted candidates per round (all ranks together); VATLQ_TARGET overrides
 constexpr int kMaxRanks = 16;
 constexpr int kMaxSmem = 220 * 1024;
 
@@ -64,7 +65,7 @@ struct Ctl {
   double wd, wu;    // score = wd*min_d + wu*unc
   double U, W;      // histogram window [U-W, U]; W <= 0: no window yet
   double theta_emit;   // the pass lists every owned row whose new score is >= theta_emit (+inf: none)
-  int emit_mode, pad2; // RankBlock::mode of that list
+  int emit_mode, target; // RankBlock::mode of that list; wanted candidates per round
   unsigned int filter_ticket, pairs_ticket;
   long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
 };
@@ -87,6 +88,62 @@ __device__ __forceinline__ Best warp_best(Best b) {
     }
   }
   return b;
+}
+
+// ---- candidate-block exchange over peer memory (NVLink) ------------------------------------
+// Every rank owns a mailbox in its own HBM: two parities of kMaxRanks block slots plus one flag
+// per source rank.  The CTA that finishes a rank's block header pushes the block (header + the
+// listed records) straight into slot [parity][rank] of EVERY rank's mailbox with peer stores,
+// fences system-wide and raises flag[rank] = sequence number in each mailbox; the kernel that
+// consumes the blocks spins on its LOCAL flags.  No collective launch sits between the pass
+// that produces the candidates and the planner that consumes them.
+struct Mailbox {
+  RankBlock slots[2][kMaxRanks];
+  unsigned long long flags[kMaxRanks];
+  unsigned long long error;      // set when a wait timed out
+};
+struct PushArgs {
+  Mailbox* const* peers;         // device array [world]: every rank's mailbox (own one included)
+  int rank, world;
+  unsigned long long seq;        // sequence number of the block being produced (parity = seq & 1)
+};
+
+// called by every thread of ONE CTA after the block header in `send` is complete
+__device__ void push_block(const PushArgs& p, const RankBlock* send) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long long cnt = min(__ldcg(&send->count), (long long)kCapL);
+  const int par = (int)(p.seq & 1ULL);
+  for (int r = 0; r < p.world; ++r) {
+    RankBlock* dst = &p.peers[r]->slots[par][p.rank];
+    // header (64 bytes) then the first `cnt` entries of the four record arrays
+    if (tid < 8) reinterpret_cast<long long*>(dst)[tid] = __ldcg(reinterpret_cast<const long long*>(send) + tid);
+    for (long long q = tid; q < cnt; q += nthr) {
+      dst->idx[q] = __ldcg(&send->idx[q]);
+      dst->m[q] = __ldcg(&send->m[q]);
+      dst->unc[q] = __ldcg(&send->unc[q]);
+      dst->score[q] = __ldcg(&send->score[q]);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < p.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)&p.peers[tid]->flags[p.rank]) = p.seq;
+  }
+}
+
+// thread 0 of a CTA waits until every rank's block `seq` has landed in the local mailbox
+__device__ __forceinline__ void wait_blocks(Mailbox* mine, int world, unsigned long long seq) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    while (*((volatile unsigned long long*)&mine->flags[r]) < seq) {
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; report instead of hanging the GPU
+        mine->error = seq;
+        return;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 __device__ __forceinline__ double score_of(int rule, double wd, double wu, double m, double u) {
@@ -270,6 +327,7 @@ struct PassArgs {
   unsigned int* hist;        // null: no histogram
   RankBlock* send;           // null: do not list candidates / arg-max (initialisation passes)
   Best* partial;             // per-CTA arg-max scratch (gridDim entries)
+  PushArgs push;             // push.peers != null: the published block is pushed to every rank's mailbox
   unsigned char* did_work;   // optional: set to 1 when this launch applied centres (pass timing bookkeeping)
   double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
 };
@@ -344,6 +402,11 @@ __device__ void publish_pass(const PassArgs& a, Best best, bool do_hist, const u
       a.send->mode = a.ctl->emit_mode;
       a.send->inwin = do_hist ? (long long)((volatile unsigned int*)a.hist)[kNB] : 0;
       a.ctl->filter_ticket = 0;
+      __threadfence();
+    }
+    if (a.push.peers != nullptr) {
+      __syncthreads();
+      push_block(a.push, a.send);
     }
   }
 }
@@ -787,7 +850,7 @@ __global__ void __launch_bounds__(256) score_init_kernel(long long lo, long long
 // ---------------------------------------------------------------- bootstrap: arg-max of the initial scores
 // Only before the first round: afterwards every pass leaves the block header behind itself.
 __global__ void __launch_bounds__(256) bootstrap_kernel(long long lo, long long hi, const double* __restrict__ score,
-                                                        Best* partial, RankBlock* out, Ctl* ctl) {
+                                                        Best* partial, RankBlock* out, Ctl* ctl, PushArgs push) {
   __shared__ Best s_best[8];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x;
@@ -833,6 +896,11 @@ __global__ void __launch_bounds__(256) bootstrap_kernel(long long lo, long long 
       out->mode = 0;
       out->inwin = 0;
       ctl->filter_ticket = 0;
+      __threadfence();
+    }
+    if (push.peers != nullptr) {
+      __syncthreads();
+      push_block(push, out);
     }
   }
 }
@@ -991,13 +1059,18 @@ template <int STEPS>
 __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* __restrict__ X, int d4,
                                                                   const double* __restrict__ xx, const RankBlock* blocks,
                                                                   RankBlock* send, unsigned int* hist, long long* out_idx,
-                                                                  Ctl* ctl, double* __restrict__ Dcc) {
+                                                                  Ctl* ctl, double* __restrict__ Dcc, Mailbox* mail,
+                                                                  unsigned long long seq) {
   __shared__ __align__(16) double s_part[2][kSeg][64];
   __shared__ double s_xxc[kB];
   __shared__ unsigned int s_last;
   if (ctl->n_picked >= ctl->k) {       // (uniform over the grid: nobody takes a ticket)
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctl->nb = 0;
     return;
+  }
+  if (mail != nullptr) {               // peer-memory exchange: the blocks of this round land in the local mailbox
+    if (threadIdx.x == 0) wait_blocks(mail, ctl->world, seq);
+    __syncthreads();
   }
   {
     const int world = ctl->world;
@@ -1144,7 +1217,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
       s_mode = 0;
     }
     __syncthreads();
-    if (windowed) choose_theta(hist, U0, W0, max(1, kTarget / max(1, world)), tid, &s_theta, &s_mode);
+    if (windowed) choose_theta(hist, U0, W0, max(1, ctl->target / max(1, world)), tid, &s_theta, &s_mode);
     __syncthreads();
     for (int k = tid; k < kNB + 1; k += blockDim.x) hist[k] = 0u;
     if (tid == 0) {
@@ -1266,7 +1339,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     const double U = ctl->U;
     double W = ctl->W;
     const double frac = (U - v.theta) / W;
-    if (inwin < kTarget) W = fmin(U, W * 4.0);
+    if (inwin < ctl->target) W = fmin(U, W * 4.0);
     else if (frac < 1.0 / 16.0) W = W * 0.5;
     else if (frac > 0.5) W = fmin(U, W * 2.0);
     ctl->U = fmax(bb.s, v.theta);
@@ -1283,6 +1356,12 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
 __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const RankBlock* blocks, RankBlock* send, const double* Dcc,
                                                             unsigned int* hist, long long* out_idx, Ctl* ctl) {
   plan_body(blocks, send, Dcc, hist, out_idx, ctl);
+}
+
+// generic-shape rounds with the peer-memory exchange: one thread waits for the round's blocks
+__global__ void wait_blocks_kernel(Mailbox* mail, const Ctl* ctl, unsigned long long seq) {
+  if (ctl->n_picked >= ctl->k) return;
+  wait_blocks(mail, ctl->world, seq);
 }
 
 // distances of every row to a list of centers, for the parity tests
@@ -1353,6 +1432,11 @@ static int load_nccl() {
 struct Comm {
   void* nccl;
   int rank, world;
+  // peer-memory mailbox (vatlq_comm_mailbox_handle / vatlq_comm_attach); null -> NCCL all-gather
+  Mailbox* mail = nullptr;           // this rank's mailbox (cudaMalloc)
+  Mailbox** peers_dev = nullptr;     // device array of every rank's mailbox pointer
+  void* opened[kMaxRanks] = {};      // cudaIpcOpenMemHandle results to close
+  unsigned long long seq = 0;        // last sequence number used (monotonic over the communicator's life)
 };
 
 // ---------------------------------------------------------------- workspace layout
@@ -1504,6 +1588,18 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   Best* partial = (Best*)(w + L.partial);
   RankBlock* send = (RankBlock*)(w + L.send);
   RankBlock* recv = (world > 1) ? (RankBlock*)(w + L.recv) : send;
+  const bool p2p = world > 1 && comm->peers_dev != nullptr;   // peer-memory mailbox instead of ncclAllGather
+  const unsigned long long seq0 = p2p ? comm->seq : 0ULL;
+  auto push_of = [&](unsigned long long seq) {
+    PushArgs pa{};
+    if (p2p) {
+      pa.peers = comm->peers_dev;
+      pa.rank = comm->rank;
+      pa.world = world;
+      pa.seq = seq;
+    }
+    return pa;
+  };
   double* Dcc = (double*)(w + L.dcc);
   unsigned char* flags = (unsigned char*)(w + L.flags);
   const Geom G = geom_of(d);
@@ -1517,6 +1613,14 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   h.wd = (rule == 0) ? (1.0 - moks) : 1.0;
   h.wu = (rule == 0) ? (lambda * moks) : lambda;
   h.U = 0.0; h.W = -1.0;
+  {
+    static const int target = []() {
+      const char* e = getenv("VATLQ_TARGET");
+      const int t = e ? atoi(e) : 0;
+      return (t >= 16 && t <= kCap) ? t : 0;
+    }();
+    h.target = target ? target : (nbk > kB ? kTarget + kTarget / 2 : kTarget);   // 16 picks per round want a longer list
+  }
   if (n_labeled == 0 && rule == 2) {
     // _query (:828-833): the caller drew the random first pick
     VQ_REQUIRE(first_pick >= 0 && first_pick < n, "rule 2 with an empty labelled set needs first_pick");
@@ -1560,7 +1664,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     }
   }
   // block header of round 0 (no list, exact arg-max); later headers come from the passes
-  bootstrap_kernel<<<fgrid, 256, 0, stream>>>(row_lo, row_hi, score, partial, send, ctl);
+  bootstrap_kernel<<<fgrid, 256, 0, stream>>>(row_lo, row_hi, score, partial, send, ctl, push_of(seq0 + 1));
   VQ_LAUNCHED();
 
   // rounds: [all-gather] -> pairs -> plan -> pass.  The host only learns the pick count every
@@ -1579,7 +1683,13 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     chunk = std::max<long long>(4, std::min<long long>(chunk, 256));
     if (g_prof.on) VQ_CUDA(cudaMemsetAsync(flags, 0, 1024, stream));
     for (long long it = 0; it < chunk && rc == 0; ++it) {
-      if (world > 1) {
+      const unsigned long long round_no = (unsigned long long)(rounds_done + it) + 1;   // 1-based over the call
+      const RankBlock* blocks = recv;
+      Mailbox* mail = nullptr;
+      if (p2p) {
+        mail = comm->mail;
+        blocks = &comm->mail->slots[(seq0 + round_no) & 1ULL][0];
+      } else if (world > 1) {
         const int e = g_nccl.AllGather(send, recv, sizeof(RankBlock), /*ncclChar*/ 0, comm->nccl, stream);
         if (e != 0) {
           snprintf(g_err, sizeof(g_err), "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
@@ -1589,18 +1699,26 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       }
       if (nbk > 1) {
         dim3 pg(kCap / kB, 4);
-        if (fast_d) pairs_plan_kernel<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, recv, send, hist, (long long*)out_idx, ctl, Dcc);
-        else pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, recv, ctl, Dcc);
+        if (fast_d) {
+          pairs_plan_kernel<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, blocks, send, hist, (long long*)out_idx, ctl, Dcc,
+                                                             mail, seq0 + round_no);
+        } else {
+          if (p2p) wait_blocks_kernel<<<1, 1, 0, stream>>>(mail, ctl, seq0 + round_no);
+          pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, blocks, ctl, Dcc);
+        }
         g_launches.fetch_add(1);
+      } else if (p2p) {
+        wait_blocks_kernel<<<1, 1, 0, stream>>>(mail, ctl, seq0 + round_no);
       }
       if (nbk == 1 || !fast_d) {
-        plan_kernel<<<1, kPlanThreads, 0, stream>>>(recv, send, Dcc, hist, (long long*)out_idx, ctl);
+        plan_kernel<<<1, kPlanThreads, 0, stream>>>(blocks, send, Dcc, hist, (long long*)out_idx, ctl);
         g_launches.fetch_add(1);
       }
       for (int off = 0; off < nbk && rc == 0; off += kB) {   // picks [off, off+8) of the round; the last pass emits
         PassArgs a{};
         fill_pass(a);
         a.center_off = off;
+        a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
         rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
@@ -1641,6 +1759,14 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       break;
     }
     picked = hc->n_picked;
+  }
+  if (p2p) {
+    comm->seq = seq0 + (unsigned long long)rounds_done + 2;
+    unsigned long long err = 0;
+    if (rc == 0 && cudaMemcpy(&err, &comm->mail->error, 8, cudaMemcpyDeviceToHost) == cudaSuccess && err != 0) {
+      snprintf(g_err, sizeof(g_err), "peer-memory exchange timed out waiting for block %llu", err);
+      rc = VATLQ_ECOMM;
+    }
   }
   if (rc == 0 && host_stats) {
     const Ctl* hc = (const Ctl*)h_picked;
@@ -1704,14 +1830,68 @@ extern "C" int vatlq_comm_init(const void* host_id128, int rank, int world, void
     snprintf(g_err, sizeof(g_err), "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
     return VATLQ_ECOMM;
   }
-  Comm* cm = new Comm{c, rank, world};
+  Comm* cm = new Comm();
+  cm->nccl = c;
+  cm->rank = rank;
+  cm->world = world;
   *comm_out = cm;
+  return 0;
+}
+
+// ---- peer-memory mailbox: each rank allocates one, exports its IPC handle, imports the others'
+extern "C" int vatlq_comm_mailbox_handle(void* comm, void* host_handle64) {
+  VQ_REQUIRE(comm && host_handle64, "null argument");
+  Comm* cm = (Comm*)comm;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!cm->mail) {
+    VQ_CUDA(cudaMalloc((void**)&cm->mail, sizeof(Mailbox)));
+    VQ_CUDA(cudaMemset(cm->mail, 0, sizeof(Mailbox)));
+  }
+  cudaIpcMemHandle_t h;
+  VQ_CUDA(cudaIpcGetMemHandle(&h, cm->mail));
+  memcpy(host_handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int vatlq_comm_attach(void* comm, const void* host_handles, int world) {
+  VQ_REQUIRE(comm && host_handles, "null argument");
+  Comm* cm = (Comm*)comm;
+  VQ_REQUIRE(world == cm->world && cm->mail != nullptr, "attach after vatlq_comm_mailbox_handle, same world size");
+  Mailbox* ptrs[kMaxRanks] = {};
+  for (int r = 0; r < world; ++r) {
+    if (r == cm->rank) {
+      ptrs[r] = cm->mail;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)host_handles + 64 * r, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      for (int q = 0; q < r; ++q)
+        if (cm->opened[q]) {
+          cudaIpcCloseMemHandle(cm->opened[q]);
+          cm->opened[q] = nullptr;
+        }
+      return VATLQ_ECOMM;
+    }
+    cm->opened[r] = p;
+    ptrs[r] = (Mailbox*)p;
+  }
+  VQ_CUDA(cudaMalloc((void**)&cm->peers_dev, sizeof(Mailbox*) * kMaxRanks));
+  VQ_CUDA(cudaMemcpy(cm->peers_dev, ptrs, sizeof(Mailbox*) * kMaxRanks, cudaMemcpyHostToDevice));
   return 0;
 }
 
 extern "C" int vatlq_comm_destroy(void* comm) {
   if (!comm) return 0;
   Comm* cm = (Comm*)comm;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (cm->opened[r]) cudaIpcCloseMemHandle(cm->opened[r]);
+  if (cm->peers_dev) cudaFree(cm->peers_dev);
+  if (cm->mail) cudaFree(cm->mail);
   if (g_nccl.CommDestroy && cm->nccl) g_nccl.CommDestroy(cm->nccl);
   delete cm;
   return 0;

@@ -83,10 +83,11 @@ def allgather_rows(local: torch.Tensor, n: int, world: int, group=None) -> torch
 class Comm:
     """Library-owned NCCL communicator (vatlq_comm_*), bootstrapped through torch.distributed."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, use_p2p: bool = True):
         self.rank = td.get_rank(group)
         self.world = td.get_world_size(group)
         self.handle = None
+        self.p2p = False
         if self.world == 1:
             return
         L = _lib.lib()
@@ -99,6 +100,23 @@ class Comm:
         out = C.c_void_p()
         _lib.check(L.vatlq_comm_init(C.cast(uid, C.c_void_p), self.rank, self.world, C.byref(out)), "vatlq_comm_init")
         self.handle = out.value
+        # peer-memory mailboxes (NVLink): exchange the IPC handles; fall back to NCCL if a peer cannot be mapped
+        self.p2p = False
+        if use_p2p:
+            hb = (C.c_char * 64)()
+            _lib.check(L.vatlq_comm_mailbox_handle(C.c_void_p(self.handle), C.cast(hb, C.c_void_p)), "vatlq_comm_mailbox_handle")
+            allh = [None] * self.world
+            td.all_gather_object(allh, bytes(hb.raw), group=group)
+            blob = (C.c_char * (64 * self.world)).from_buffer_copy(b"".join(allh))
+            rc = L.vatlq_comm_attach(C.c_void_p(self.handle), C.cast(blob, C.c_void_p), self.world)
+            ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+            td.all_reduce(ok, op=td.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.p2p = True
+            elif rc == 0:
+                raise _lib.VatlqError("peer-memory attach succeeded here but failed on another rank")
+            else:
+                _lib.check(rc, "vatlq_comm_attach")
 
     def close(self):
         if self.handle:

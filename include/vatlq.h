@@ -155,6 +155,48 @@ int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64
 int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,
                         double* out, void* ws /* >= n*8 bytes */, size_t ws_bytes, vatlq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * SURVEY.md 8f "next" rows: the other per-item uncertainties and the representativeness step.
+ *
+ * vatlq_pose_unc — pose-level uncertainties from the scan's outputs (no second pass over H):
+ *   hp[n]  fp32  HP  = float(-np.sum(pose_scores))            ActiveLearning.py:329-330
+ *   tpc[n] fp32  TPC = #joints that moved more than 0.01*sqrt(box area) between frame t and
+ *                t-1 / t+1, the neighbour decoded with frame t's crop box, doubled when only
+ *                one neighbour exists                          ActiveLearning.py:333-344,736-745
+ *   coords_hm[n,J,2] / kpts[n,J,3] as written by vatlq_heatmap_scan; halo_*_xy: optional
+ *   (J,2) heat-map-space coordinates of the frames next to the range (shards / chunks).
+ * vatlq_heatmap_entropy — Entropy = sum_j scipy.stats.entropy(H[t,j].flatten()), fp32
+ *   (ActiveLearning.py:790-796; -inf when a map holds negative values, NaN when it sums to 0);
+ *   one streaming pass, ws >= n*J*4 bytes.
+ * ------------------------------------------------------------------------------------ */
+int vatlq_pose_unc(const float* coords_hm, const float* kpts, const float* bbox_xyxy,
+                   const uint8_t* is_prev, const uint8_t* is_next, int64_t n, int J, int h, int w,
+                   const float* halo_prev_xy, const float* halo_next_xy, float* hp, float* tpc,
+                   vatlq_stream_t stream);
+int vatlq_heatmap_entropy(const float* H, int64_t n, int J, int h, int w, float* entropy,
+                          void* ws, size_t ws_bytes, vatlq_stream_t stream);
+
+/* Influence (ActiveLearning.py:467-477) and Diversity (:581-590): row sums of the cosine-distance
+ * matrix that KNeighborsTransformer(mode='distance', metric='cosine', n_neighbors=m-1) builds
+ * over the rows X[rows[0..m)] (rows == NULL: all n rows, m == n), via
+ *   sum_j (1 - xh_i . xh_j) = m_total - xh_i . S,   S = sum_j xh_j,  xh = x / |x|   (fp64)
+ * Two calls so that a multi-GPU caller can all-reduce S (SUM) in between:
+ *   colsum: S[d] over this rank's rows;  rowsum: out[m] = m_total - (x_i . S) / |x_i|.
+ * d must be a multiple of 4 and <= 2048; ws from vatlq_cosine_workspace_bytes(d). */
+size_t vatlq_cosine_workspace_bytes(int d);
+int vatlq_cosine_colsum(const float* X, int64_t n, int d, const int64_t* rows, int64_t m,
+                        double* S, void* ws, size_t ws_bytes, vatlq_stream_t stream);
+int vatlq_cosine_rowsum(const float* X, int64_t n, int d, const int64_t* rows, int64_t m,
+                        const double* S, double m_total, double* out, vatlq_stream_t stream);
+
+/* stats2[2] = {min v, -max v} over rows with mask != 0 (mask NULL: all rows): the statistics
+ * vatlq_fuse_final consumes, for fp64 score vectors (influence normalisation, :477). */
+int vatlq_minmax_stats_f64(const double* v, const uint8_t* mask, int64_t n, double* stats2,
+                           vatlq_stream_t stream);
+/* out_i = cw*unc_i + (1-cw)*infl_i on rows with mask != 0, else 0 (ActiveLearning.py:519). */
+int vatlq_fuse_blend(const double* unc, const double* infl, const uint8_t* mask, int64_t n,
+                     double combine_weight, double* out, vatlq_stream_t stream);
+
 /* Timing of the dominant kernel (the pass over X) for bench.py's roofline: when enabled,
  * vatlq_coreset_select brackets every pass launch with CUDA events on `stream`; read returns
  * the summed duration of the passes that applied picks, their number and the picks applied.

@@ -103,6 +103,89 @@ def edge_maps():
     return np.stack(frames).astype(np.float32)
 
 
+def pin_next_rows(R, O, synth):
+    """HP / TPC / Entropy (reference methods compute_tpc / compute_entropy
+    called unbound; the HP expression of :330 evaluated as written), Influence / Diversity /
+    top-k (the sklearn calls of :469-477, :527-540, :581-590 evaluated as written)."""
+    from sklearn.neighbors import KNeighborsTransformer
+    rng = np.random.default_rng(21)
+    n = 14
+    ids, ip, inx = synth.track_flags(n, rng, mean_len=5.0)
+    H = synth.heatmaps(n, seed=21, track_ids=ids)
+    # make TPC discriminative: inside a track most joints stay put, a few move by whole pixels
+    for i in range(1, n):
+        if ip[i]:
+            H[i] = H[i - 1] + rng.normal(0, 1e-4, H[i].shape).astype(np.float32)
+            for j in rng.choice(17, size=int(rng.integers(0, 6)), replace=False):
+                H[i, j] = np.roll(H[i - 1, j], (int(rng.integers(-2, 3)), int(rng.integers(-2, 3))), axis=(0, 1))
+    boxes = synth.boxes_xyxy(n, seed=21)
+    fake = SimpleNamespace(heatmap_to_coord=R.heatmap_to_coord_simple, eval_joints=list(range(17)),
+                           hm_size=[64, 48], norm_type=None)
+    hp_ref, tpc_ref, ent_ref, ent_pos_ref = [], [], [], []
+    Hpos = np.abs(H) + np.float32(1e-3)          # a non-negative pool: finite entropies
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(n):
+            box = boxes[i].tolist()
+            pose_coords, pose_scores = R.heatmap_to_coord_simple(H[i], box)
+            hp_ref.append(float(-np.sum(pose_scores)))                                   # :330
+            thresh = 0.01 * np.sqrt((box[2] - box[0]) * (box[3] - box[1]))               # :334
+            tpc = 0
+            has_p, has_n = bool(ip[i]) and i > 0, bool(inx[i]) and i < n - 1
+            if has_p:
+                tpc += R.AL.compute_tpc(fake, pose_coords, H[i - 1], box, thresh)
+            if has_n:
+                tpc += R.AL.compute_tpc(fake, pose_coords, H[i + 1], box, thresh)
+                if not has_p:
+                    tpc *= 2
+            elif has_p:
+                tpc *= 2
+            tpc_ref.append(float(tpc))
+            ent_ref.append(float(R.AL.compute_entropy(fake, H[i])))
+            ent_pos_ref.append(float(R.AL.compute_entropy(fake, Hpos[i])))
+        same(hp_ref, O.pose_unc_pool(H, boxes, ip, inx, "HP"), "HP")
+        same(tpc_ref, O.pose_unc_pool(H, boxes, ip, inx, "TPC"), "TPC")
+        same(ent_ref, O.pose_unc_pool(H, boxes, ip, inx, "Entropy"), "Entropy raw")
+        same(ent_pos_ref, O.pose_unc_pool(Hpos, boxes, ip, inx, "Entropy"), "Entropy positive")
+    assert len(set(tpc_ref)) > 3, tpc_ref
+
+    # Influence / Diversity / top-k on clustered and i.i.d. embeddings
+    out = dict(H=H, boxes=boxes, is_prev=ip, is_next=inx, hp=np.array(hp_ref), tpc=np.array(tpc_ref),
+               entropy_raw=np.array(ent_ref), entropy_pos=np.array(ent_pos_ref))
+    for tag, clustered in (("clu", True), ("iid", False)):
+        N, k = 400, 20
+        X32 = synth.embeddings(N, d=256, seed=31 + clustered, clustered=clustered)
+        X = X32.astype(np.float64)
+        lab = sorted(rng.choice(N, 60, replace=False).tolist())
+        unl = [i for i in range(N) if i not in set(lab)]
+        unc_score = rng.uniform(0, 1, len(unl))
+        cw = 0.37
+        knn = KNeighborsTransformer(mode="distance", metric="cosine", n_neighbors=len(unl) - 1)   # :471
+        infl = np.asarray(np.sum(knn.fit_transform(X[unl]), axis=1)).flatten()                  # :472-473
+        rowsum_ref = infl.copy()
+        infl = (infl - np.min(infl)) / (np.max(infl) - np.min(infl))                            # :475
+        same(infl, O.influence_scores(X, unl), f"influence {tag}")
+        total = cw * unc_score + (1 - cw) * infl                                                # :519
+        same(total, O.total_score(unc_score, infl, cw), f"total {tag}")
+        score_dict = dict((idx, sc) for idx, sc in zip(unl, total))                              # :527
+        srt = sorted(score_dict.items(), key=lambda x: x[1], reverse=True)                       # :529
+        score_dict = dict((int(idx), sc) for idx, sc in srt)
+        top_ref = sorted(list(score_dict.keys())[:k])                                            # :534
+        same(top_ref, O.topk_select(unl, total, k), f"topk {tag}")
+        cand = sorted(list(score_dict.keys())[:8 * k])                                           # :538
+        knn = KNeighborsTransformer(mode="distance", metric="cosine", n_neighbors=len(cand) - 1)  # :583
+        div = np.asarray(np.sum(knn.fit_transform(X[cand]), axis=1)).flatten()
+        dd = dict((idx, sc) for idx, sc in zip(cand, div))
+        dd = dict((int(idx), sc) for idx, sc in sorted(dd.items(), key=lambda x: x[1]))          # :587-588
+        div_ref = list(dd.keys())[:k]                                                            # :589
+        same(div_ref, O.diversity_select(X, unl, total, k), f"diversity {tag}")
+        out.update({f"{tag}_X": X32, f"{tag}_labeled": np.array(lab, np.int64), f"{tag}_unc": unc_score,
+                    f"{tag}_cw": np.float64(cw), f"{tag}_k": np.int64(k), f"{tag}_rowsum": rowsum_ref,
+                    f"{tag}_influence": infl, f"{tag}_total": total, f"{tag}_topk": np.array(top_ref, np.int64),
+                    f"{tag}_div_rowsum": div, f"{tag}_diversity": np.array(div_ref, np.int64)})
+    np.savez_compressed(os.path.join(GOLD, "next.npz"), **out)
+
+
 def main():
     from oracle import vatl_oracle as O
     synth = importlib.import_module("vatl4pose-wacv2024_b200.synth")
@@ -250,6 +333,7 @@ def main():
         for key, val in c.items():
             flat[f"{tag}/{key}"] = np.asarray(val)
     np.savez_compressed(os.path.join(GOLD, "coreset.npz"), **flat)
+    pin_next_rows(R, O, synth)
     print("oracle pinned against the reference; fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(f"  {fn}: {os.path.getsize(os.path.join(GOLD, fn)) / 1e6:.2f} MB")

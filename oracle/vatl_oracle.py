@@ -310,6 +310,117 @@ def coreset_select(X: np.ndarray, unc: np.ndarray, labeled, k: int, moks: float,
 
 
 # --------------------------------------------------------------------------------------
+# SURVEY.md §8f "next" rows: HP / TPC / Entropy uncertainties, Influence, Diversity, top-k
+# --------------------------------------------------------------------------------------
+
+def hp_item(pose_scores) -> float:
+    """active_learning/ActiveLearning.py:329-330 — highest-probability uncertainty: minus the
+    sum of the 17 peak values (fp32 numpy sum over the (17,1) maxvals array)."""
+    return float(-np.sum(pose_scores))
+
+
+def tpc_pair(cur_pose: np.ndarray, adj_hm: np.ndarray, bbox_xyxy, thresh) -> int:
+    """active_learning/ActiveLearning.py:736-745 (compute_tpc) — joints whose image-space
+    position differs by more than `thresh` between the current pose and the pose decoded from
+    the adjacent frame's heat maps with the CURRENT crop box."""
+    adj_pose, _ = heatmap_to_coord(adj_hm, bbox_xyxy)
+    dist = np.linalg.norm(cur_pose - adj_pose, axis=1)
+    return np.count_nonzero(dist > thresh)
+
+
+def tpc_item(cur_pose, prev_hm, next_hm, bbox_xyxy, has_prev: bool, has_next: bool) -> float:
+    """Call-site logic active_learning/ActiveLearning.py:333-344."""
+    thresh = 0.01 * np.sqrt((bbox_xyxy[2] - bbox_xyxy[0]) * (bbox_xyxy[3] - bbox_xyxy[1]))
+    tpc = 0
+    if has_prev:
+        tpc += tpc_pair(cur_pose, prev_hm, bbox_xyxy, thresh)
+    if has_next:
+        tpc += tpc_pair(cur_pose, next_hm, bbox_xyxy, thresh)
+        if not has_prev:
+            tpc *= 2
+    elif has_prev:
+        tpc *= 2
+    return float(tpc)
+
+
+def entropy_item(hm: np.ndarray) -> float:
+    """active_learning/ActiveLearning.py:790-796 (compute_entropy) — sum over the joints of
+    scipy.stats.entropy of the flattened (raw, un-normalised) map."""
+    from scipy.stats import entropy
+    total = 0
+    for m in hm:
+        total += entropy(m.flatten())
+    return float(total)
+
+
+def pose_unc_pool(H, boxes_xyxy, is_prev, is_next, kind: str) -> np.ndarray:
+    """HP / TPC / Entropy of every item of an id-sorted pool (neighbours from the pool itself,
+    like thc_pool).  float64 vector of the `float(uncertainty)` values."""
+    n = H.shape[0]
+    out = np.zeros(n, dtype=np.float64)
+    for i in range(n):
+        box = [float(v) for v in boxes_xyxy[i]]
+        if kind == "Entropy":
+            out[i] = entropy_item(H[i])
+            continue
+        pose, scores = heatmap_to_coord(H[i], box)
+        if kind == "HP":
+            out[i] = hp_item(scores)
+        elif kind == "TPC":
+            hp_ = bool(is_prev[i]) and i > 0
+            hn_ = bool(is_next[i]) and i < n - 1
+            out[i] = tpc_item(pose, H[i - 1] if hp_ else None, H[i + 1] if hn_ else None, box, hp_, hn_)
+        else:
+            raise ValueError(kind)
+    return out
+
+
+def cosine_rowsum(Xs: np.ndarray) -> np.ndarray:
+    """active_learning/ActiveLearning.py:471-475 and :582-585 — row sums of the distance graph
+    KNeighborsTransformer(mode='distance', metric='cosine', n_neighbors=m-1) builds over Xs."""
+    from sklearn.neighbors import KNeighborsTransformer
+    knn = KNeighborsTransformer(mode="distance", metric="cosine", n_neighbors=len(Xs) - 1)
+    graph = knn.fit_transform(Xs)
+    return np.asarray(np.sum(graph, axis=1)).flatten()
+
+
+def influence_scores(X: np.ndarray, unlabeled_idx) -> np.ndarray:
+    """active_learning/ActiveLearning.py:468-477 — min-max normalised cosine row sums over the
+    unlabelled items; zeros when |U| <= 1."""
+    if len(unlabeled_idx) in (0, 1):
+        return np.zeros(len(unlabeled_idx))
+    s = cosine_rowsum(X[unlabeled_idx])
+    return _minmax(s)
+
+
+def total_score(unc_score, influence, combine_weight):
+    """active_learning/ActiveLearning.py:517-526."""
+    if unc_score is not None and influence is not None:
+        return combine_weight * unc_score + (1 - combine_weight) * influence
+    return unc_score if unc_score is not None else influence
+
+
+def candidate_order(unlabeled_idx, total):
+    """active_learning/ActiveLearning.py:527-530 — unlabelled ids by descending score (stable)."""
+    d = dict((idx, sc) for idx, sc in zip(unlabeled_idx, total))
+    return [int(i) for i, _ in sorted(d.items(), key=lambda x: x[1], reverse=True)]
+
+
+def topk_select(unlabeled_idx, total, k: int):
+    """filter == "None" (:533-534,541-542): the k best ids, returned sorted ascending."""
+    return sorted(candidate_order(unlabeled_idx, total)[:k])
+
+
+def diversity_select(X: np.ndarray, unlabeled_idx, total, k: int):
+    """filter == "Diversity" (:537-538,581-590): the 8k best ids (sorted ascending) re-ranked by
+    ascending cosine row sum among themselves; the first k."""
+    cand = sorted(candidate_order(unlabeled_idx, total)[:8 * k])
+    div = cosine_rowsum(X[cand])
+    d = dict((idx, sc) for idx, sc in zip(cand, div))
+    return [int(i) for i, _ in sorted(d.items(), key=lambda x: x[1])][:k]
+
+
+# --------------------------------------------------------------------------------------
 # whole scoring loop (the CPU arm that bench.py times)
 # --------------------------------------------------------------------------------------
 

@@ -43,6 +43,11 @@ def gold_fuse():
 
 
 @pytest.fixture(scope="session")
+def gold_next():
+    return load_golden("next.npz")
+
+
+@pytest.fixture(scope="session")
 def gold_coreset():
     z = load_golden("coreset.npz")
     cases = {}

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(built_lib):
     from vatlq import _lib
     names = declared_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 25
     h = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(h, n), f"{n} declared in include/vatlq.h but not exported"
@@ -99,15 +99,18 @@ def test_strategy_names_and_errors():
         with pytest.raises(ValueError):
             ActiveLearning(*_cfg_opt(*bad), eval_len=10)
     # names that exist in the reference but are not accelerated dispatch back to the reference
-    for u in ("HP", "TPC", "MPE", "Entropy", "Margin"):
+    for u in ("MPE", "Margin", "VL4Pose"):
         al = ActiveLearning(*_cfg_opt(u), eval_len=10)
         with pytest.raises(NotImplementedError):
             al._require_accelerated()
-    al = ActiveLearning(*_cfg_opt("THC", "Influence", "None"), eval_len=10)
-    with pytest.raises(NotImplementedError):
-        al._require_accelerated()
-    for u in ("THC", "THC_L1", "WPU", "WPU_hybrid", "THC+WPU", "None"):
+    for f in ("weighted", "K-Means"):
+        al = ActiveLearning(*_cfg_opt("THC", "None", f), eval_len=10)
+        with pytest.raises(NotImplementedError):
+            al._require_accelerated()
+    for u in ("THC", "THC_L1", "WPU", "WPU_hybrid", "THC+WPU", "None", "HP", "TPC", "Entropy"):
         ActiveLearning(*_cfg_opt(u), eval_len=10)._require_accelerated()
+    for r, f in (("Influence", "None"), ("Random", "Diversity"), ("None", "Random"), ("Influence", "Coreset")):
+        ActiveLearning(*_cfg_opt("THC", r, f), eval_len=10)._require_accelerated()
 
 
 def test_outcome_bookkeeping():

@@ -84,3 +84,36 @@ def test_coreset_matches_reference(gold_coreset):
                                      float(c["moks"]), float(c["lam"]), str(c["rule"]))
         assert picks == c["picks"].tolist(), tag
         assert np.array_equal(md, c["min_d"]), tag
+
+
+# ---- HP / TPC / Entropy, Influence / Diversity / top-k ----------------
+def test_next_row_uncertainties_match_reference(gold_next):
+    g = gold_next
+    H, boxes, ip, inx = g["H"], g["boxes"], g["is_prev"], g["is_next"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert np.array_equal(O.pose_unc_pool(H, boxes, ip, inx, "HP"), g["hp"])
+        assert np.array_equal(O.pose_unc_pool(H, boxes, ip, inx, "TPC"), g["tpc"])
+        assert np.array_equal(O.pose_unc_pool(H, boxes, ip, inx, "Entropy"), g["entropy_raw"], equal_nan=True)
+        Hpos = np.abs(H) + np.float32(1e-3)
+        assert np.array_equal(O.pose_unc_pool(Hpos, boxes, ip, inx, "Entropy"), g["entropy_pos"])
+    assert np.isneginf(g["entropy_raw"]).all()          # raw maps hold negatives: entr(p<0) = -inf
+    assert np.isfinite(g["entropy_pos"]).all()
+    assert len(set(g["tpc"].tolist())) > 3
+
+
+def test_influence_diversity_topk_match_reference(gold_next):
+    g = gold_next
+    for tag in ("clu", "iid"):
+        X = g[f"{tag}_X"].astype(np.float64)
+        lab = set(g[f"{tag}_labeled"].tolist())
+        unl = [i for i in range(X.shape[0]) if i not in lab]
+        k, cw = int(g[f"{tag}_k"]), float(g[f"{tag}_cw"])
+        assert np.array_equal(O.cosine_rowsum(X[unl]), g[f"{tag}_rowsum"])
+        infl = O.influence_scores(X, unl)
+        assert np.array_equal(infl, g[f"{tag}_influence"])
+        total = O.total_score(g[f"{tag}_unc"], infl, cw)
+        assert np.array_equal(total, g[f"{tag}_total"])
+        assert O.topk_select(unl, total, k) == g[f"{tag}_topk"].tolist()
+        assert O.diversity_select(X, unl, total, k) == g[f"{tag}_diversity"].tolist()
+    assert O.influence_scores(np.zeros((3, 8)), [1]).tolist() == [0.0]

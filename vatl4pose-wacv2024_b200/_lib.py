@@ -29,6 +29,13 @@ SIGNATURES = {
     "vatlq_coreset_select": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _dbl, _dbl, _i64,
                                     _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vatlq_pairwise_dist": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vatlq_pose_unc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "vatlq_heatmap_entropy": (_int, [_vp, _i64, _int, _int, _int, _vp, _vp, _sz, _vp]),
+    "vatlq_cosine_workspace_bytes": (_sz, [_int]),
+    "vatlq_cosine_colsum": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vatlq_cosine_rowsum": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _dbl, _vp, _vp]),
+    "vatlq_minmax_stats_f64": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "vatlq_fuse_blend": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
     "vatlq_profile_passes": (_int, [_int]),
     "vatlq_profile_read": (_int, [_vp, _vp, _vp, _int]),
     "vatlq_comm_unique_id": (_int, [_vp]),

@@ -11,9 +11,11 @@ evaluation, plotting) is out of scope and is injected or hooked:
     al.outcome()                 # bookkeeping of :166-205 without the retraining
 
 Strategy names are the reference's (`opt.uncertainty`, `opt.representativeness`, `opt.filter`,
-ActiveLearning.py:329-401,467-481,533-619).  THC*, WPU*, THC+WPU and None with filter None or
-Coreset run here; any other name raises NotImplementedError naming the reference code path to
-use (dispatch to the reference, never a CPU re-implementation of ours).
+ActiveLearning.py:329-401,467-481,533-619).  Uncertainties THC*, WPU*, THC+WPU, HP, TPC, Entropy
+and None, representativeness None / Influence / Random and filters None / Coreset / Diversity /
+Random run here; any other name (MPE, Margin, VL4Pose; weighted, K-Means) raises
+NotImplementedError naming the reference code path to use (dispatch to the reference, never a
+CPU re-implementation of ours).
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ import torch.nn as nn
 from . import _lib, ops
 from .query import QueryPass
 
-__all__ = ["ActiveLearning", "IndexCollection", "WholeBodyAE", "compute_thc", "localpeak_mean",
+__all__ = ["ActiveLearning", "IndexCollection", "WholeBodyAE", "compute_thc", "compute_entropy", "localpeak_mean",
            "heatmap_to_coord_simple", "compute_hybrid", "coreset_selection"]
 
 
@@ -62,6 +64,11 @@ def localpeak_mean(heatmaps, filter_size=3, order=0.5):
     if filter_size != 3 or order != 0.5:
         raise NotImplementedError("the query path uses filter_size=3, order=0.5 (ActiveLearning.py:412)")
     return float(ops.heatmap_scan(_as_cuda(heatmaps)[None]).peak_mean[0])
+
+
+def compute_entropy(heatmaps):
+    """ActiveLearning.compute_entropy (ActiveLearning.py:790-796) for one (J,H,W) stack."""
+    return float(ops.heatmap_entropy(_as_cuda(heatmaps)[None])[0])
 
 
 def heatmap_to_coord_simple(hms, bbox, hms_flip=None, **kwargs):
@@ -193,7 +200,8 @@ def coreset_selection(self, embeddings, uncertainty):
 # the controller
 # ----------------------------------------------------------------------------------------
 
-_REFERENCE_ONLY_UNC = ("HP", "TPC", "MPE", "VL4Pose", "Entropy", "Margin")
+_REFERENCE_ONLY_UNC = ("MPE", "VL4Pose", "Margin")     # need skimage.peak_local_max / the unfinished VL4Pose stub
+_SINGLE_UNC = ("HP", "TPC", "Entropy")
 
 
 class ActiveLearning:
@@ -218,7 +226,7 @@ class ActiveLearning:
         self.oks_fn, self.eval_hook, self.retrain_hook = oks_fn, eval_hook, retrain_hook
         # dispatch keys: accept exactly the reference's names (:329-401,467-481,533-619)
         u = self.uncertainty
-        known = u in ("None", "THC+WPU") or "THC" in u or "WPU" in u or u in _REFERENCE_ONLY_UNC
+        known = u in ("None", "THC+WPU") or "THC" in u or "WPU" in u or u in _REFERENCE_ONLY_UNC or u in _SINGLE_UNC
         if not known:
             raise ValueError("Uncertainty type is not supported")
         if self.representativeness not in ("None", "Influence", "Random"):
@@ -252,11 +260,8 @@ class ActiveLearning:
             raise NotImplementedError(
                 f"uncertainty '{u}' is not on the accelerated path: run the reference's "
                 "ActiveLearning.eval_and_query (active_learning/ActiveLearning.py:329-401) for it")
-        if self.representativeness != "None":
-            raise NotImplementedError("representativeness '%s': use the reference (ActiveLearning.py:467-483)"
-                                      % self.representativeness)
-        if self.filter not in ("None", "Coreset"):
-            raise NotImplementedError("filter '%s': use the reference (ActiveLearning.py:541-619)" % self.filter)
+        if self.filter not in ("None", "Coreset", "Diversity", "Random"):
+            raise NotImplementedError("filter '%s': use the reference (ActiveLearning.py:553-608)" % self.filter)
 
     @torch.no_grad()
     def eval_and_query(self):
@@ -265,10 +270,11 @@ class ActiveLearning:
         self._require_accelerated()
         dev = _dev()
         n = self.eval_len
-        use_wpu = "WPU" in self.uncertainty
+        use_wpu = "WPU" in self.uncertainty and self.uncertainty not in _SINGLE_UNC
         want_feat = self.filter not in ("None", "Random")   # (:283)
         qp = QueryPass(n, dev, ae_weights=self.AE if use_wpu else None, uncertainty=self.uncertainty)
-        X = torch.zeros((n, 2048), dtype=torch.float32, device=dev) if want_feat else None
+        # the reference keeps an all-zero fvecs_matrix when no filter needs embeddings (:270,283)
+        X = torch.zeros((n, 2048), dtype=torch.float32, device=dev) if (want_feat or self.representativeness == "Influence") else None
         m = self.model
         if hasattr(m, "eval"):
             m.eval()
@@ -317,8 +323,8 @@ class ActiveLearning:
         if self.uncertainty == "THC+WPU":
             total_unc = float(thc_h.astype(np.float64).sum())
             UNC = {i: [float(thc_h[i]), float(wpu_h[i])] for i in range(n)}
-        elif qp.use_thc or qp.use_wpu:
-            v = thc_h if qp.use_thc else wpu_h
+        elif qp.use_thc or qp.use_wpu or qp.single:
+            v = qp.single_score().cpu().numpy() if qp.single else (thc_h if qp.use_thc else wpu_h)
             total_unc = float(v.astype(np.float64).sum())
             UNC = {i: float(v[i]) for i in range(n)}
         else:
@@ -326,22 +332,54 @@ class ActiveLearning:
         self.uncertainty_mean.append(total_unc / n)                                   # (:466)
         self.percentage.append(len(self.labeled_id) / n * 100)
         score = qp.fuse(unl, getattr(self.opt, "THCvsWPU", "const"), labeled_ratio=len(self.labeled_id) / n)
+        if self.representativeness != "None":                                         # (:467-483)
+            unl_t = torch.as_tensor(unl_idx, dtype=torch.int64, device=dev)
+            infl = torch.zeros(n, dtype=torch.float64, device=dev)
+            if len(unl_idx) in (0, 1):
+                infl_u = np.zeros(len(unl_idx))
+            elif self.representativeness == "Influence":
+                rs = ops.cosine_rowsum(X, rows=unl_t)                                 # row sums of the cosine graph (:471-473)
+                infl[unl_t] = ops.minmax_f64(rs)                                      # (:475)
+                infl_u = infl[unl_t].cpu().numpy()
+            else:                                                                     # "Random" (:476-477)
+                infl_u = np.random.rand(len(unl_idx))
+                infl[unl_t] = torch.from_numpy(infl_u).to(dev)
+            self.influence_dict["Round" + str(self.round_cnt)] = dict(zip(map(int, unl_idx), map(float, infl_u)))
+            if len(unl_idx) not in (0, 1):
+                if self.uncertainty != "None":                                        # (:517-519)
+                    score = ops.blend_scores(score, infl, qp.combine_weight, unl)
+                else:                                                                 # (:525-526)
+                    score = infl
         if len(unl_idx) > 0:
             self.combine_weight.append(qp.combine_weight)                             # (:486-488)
         if self.uncertainty != "None" and len(unl_idx) not in (0, 1):
             self.uncertainty_dict["Round" + str(self.round_cnt)] = UNC                # (:510,514)
-        if len(unl_idx) in (0, 1) or self.filter == "None":
-            # top query_size by score, ties in unlabelled-id order (sorted() is stable) (:527-540)
+        s = order = None
+        if len(unl_idx) in (0, 1) or self.filter in ("None", "Diversity", "Random"):
+            # unlabelled ids by descending score, ties in id order (sorted() is stable) (:527-530)
             s = score.cpu().numpy()[unl_idx] if unl_idx else np.zeros(0)
             order = sorted(range(len(unl_idx)), key=lambda t: s[t], reverse=True)
+        if len(unl_idx) in (0, 1) or self.filter == "None":                           # (:533-534,541-542)
             query_list = sorted(int(unl_idx[t]) for t in order[:self.query_size])
+        elif self.filter == "Diversity":                                              # (:537-538,581-590)
+            cand = sorted(int(unl_idx[t]) for t in order[:8 * self.query_size])
+            div = ops.cosine_rowsum(X, rows=torch.as_tensor(cand, dtype=torch.int64, device=dev)).cpu().numpy()
+            by_div = sorted(range(len(cand)), key=lambda t: div[t])
+            query_list = [cand[t] for t in by_div[:self.query_size]]
+        elif self.filter == "Random":                                                 # (:591-592, random_query :727-734)
+            cand = sorted(int(unl_idx[t]) for t in order[:8 * self.query_size])
+            query_list = []
+            while len(query_list) < self.query_size and len(cand) > 0:
+                q = int(np.random.choice(cand))
+                query_list.append(q)
+                cand.remove(q)
         else:                                                                          # Coreset (:609-614)
             holder = SimpleNamespace(labeled_id=self.labeled_id, moks_queried=self.moks_queried,
                                      unc_lambda=self.unc_lambda, uncertainty=self.uncertainty, cfg=self.cfg,
                                      opt=self.opt, query_size=self.query_size, coreset_batch=self.coreset_batch)
             query_list = coreset_selection(holder, X, score)
             self.coreset_stats = holder.coreset_stats
-        self.last_query = SimpleNamespace(thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts,
+        self.last_query = SimpleNamespace(thc=qp.thc, wpu=qp.wpu, single=qp.aux, peak_mean=qp.peak_mean, kpts=qp.kpts,
                                           score=score, query_list=list(query_list))
         if len(unl_idx) != 0:                                                          # (:629-637)
             if self.oks_fn is not None:

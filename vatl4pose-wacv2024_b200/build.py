@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvatlq.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "heatmap_scan.cu", "wpu.cu", "fuse.cu", "coreset.cu"]
+SOURCES = ["api.cu", "heatmap_scan.cu", "wpu.cu", "fuse.cu", "coreset.cu", "next_rows.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
 

@@ -256,3 +256,112 @@ def pairwise_dist(X: torch.Tensor, centers) -> torch.Tensor:
         _lib.check(_lib.lib().vatlq_pairwise_dist(_ptr(X), n, d, _ptr(c), c.numel(), _ptr(out), _ptr(ws), n * 8, _stream()),
                    "vatlq_pairwise_dist")
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# SURVEY.md §8f "next" rows: HP / TPC / Entropy uncertainties, Influence / Diversity scores
+# ----------------------------------------------------------------------------------------
+
+def pose_uncertainty(coords_hm: torch.Tensor, kpts: torch.Tensor, boxes_xyxy: torch.Tensor, is_prev=None, is_next=None,
+                     hm_shape=(HM_H, HM_W), halo_prev_xy: torch.Tensor | None = None,
+                     halo_next_xy: torch.Tensor | None = None, want_hp: bool = True, want_tpc: bool = True):
+    """HP (ActiveLearning.py:329-330) and TPC (:333-344,736-745) of every item from the scan's
+    outputs (vatlq_pose_unc).  Returns (hp, tpc), fp32 (n,) CUDA tensors (None when not wanted)."""
+    kpts = _cuda(kpts, torch.float32, "kpts")
+    n, nj = kpts.shape[0], kpts.shape[1]
+    dev = kpts.device
+    xy = _cuda(coords_hm, torch.float32, "coords_hm")
+    bb = _cuda(boxes_xyxy.to(dev), torch.float32, "boxes_xyxy")
+    if tuple(xy.shape) != (n, nj, 2) or tuple(bb.shape) != (n, 4):
+        raise _lib.VatlqError("coords_hm must be (n,J,2) and boxes_xyxy (n,4)")
+    ip = _flags(is_prev, n, dev, "is_prev")
+    inx = _flags(is_next, n, dev, "is_next")
+    hpx = None if halo_prev_xy is None else _cuda(halo_prev_xy, torch.float32, "halo_prev_xy")
+    hnx = None if halo_next_xy is None else _cuda(halo_next_xy, torch.float32, "halo_next_xy")
+    for t, nm in ((hpx, "halo_prev_xy"), (hnx, "halo_next_xy")):
+        if t is not None and t.numel() != nj * 2:
+            raise _lib.VatlqError(f"{nm} must be (J,2)")
+    hp = torch.empty(n, dtype=torch.float32, device=dev) if want_hp else None
+    tpc = torch.empty(n, dtype=torch.float32, device=dev) if want_tpc else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vatlq_pose_unc(_ptr(xy), _ptr(kpts), _ptr(bb), _ptr(ip), _ptr(inx), n, nj,
+                                             int(hm_shape[0]), int(hm_shape[1]), _ptr(hpx), _ptr(hnx), _ptr(hp),
+                                             _ptr(tpc), _stream()), "vatlq_pose_unc")
+    return hp, tpc
+
+
+def heatmap_entropy(H: torch.Tensor) -> torch.Tensor:
+    """Entropy uncertainty (ActiveLearning.py:790-796) of every frame (vatlq_heatmap_entropy)."""
+    H = _cuda(H, torch.float32, "H")
+    if H.dim() != 4:
+        raise _lib.VatlqError("H must be (n,J,h,w)")
+    n, nj, h, w = H.shape
+    out = torch.empty(n, dtype=torch.float32, device=H.device)
+    ws = torch.empty(max(n * nj, 1), dtype=torch.float32, device=H.device)
+    with torch.cuda.device(H.device):
+        _lib.check(_lib.lib().vatlq_heatmap_entropy(_ptr(H), n, nj, h, w, _ptr(out), _ptr(ws), ws.numel() * 4, _stream()),
+                   "vatlq_heatmap_entropy")
+    return out
+
+
+def cosine_rowsum(X: torch.Tensor, rows=None, group=None) -> torch.Tensor:
+    """Row sums of the cosine-distance matrix of X[rows] (all rows when None): the Influence score
+    before normalisation (ActiveLearning.py:471-475) / the Diversity score (:582-585), fp64 (m,).
+    `group`: ranks hold disjoint row sets of one pool; the column sums are all-reduced."""
+    X = _cuda(X, torch.float32, "X")
+    n, d = X.shape
+    dev = X.device
+    r = None
+    m = n
+    if rows is not None:
+        r = rows if isinstance(rows, torch.Tensor) else torch.as_tensor(np.asarray(rows, dtype=np.int64))
+        r = r.to(device=dev, dtype=torch.int64).contiguous()
+        m = r.numel()
+    L = _lib.lib()
+    ws_bytes = L.vatlq_cosine_workspace_bytes(d)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    S = torch.empty(d, dtype=torch.float64, device=dev)
+    out = torch.empty(m, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.vatlq_cosine_colsum(_ptr(X), n, d, _ptr(r), m, _ptr(S), _ptr(ws), ws_bytes, _stream()),
+                   "vatlq_cosine_colsum")
+        m_total = m
+        if group is not None:
+            torch.distributed.all_reduce(S, group=group)
+            cnt = torch.tensor([m], dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(cnt, group=group)
+            m_total = int(cnt.item())
+        _lib.check(L.vatlq_cosine_rowsum(_ptr(X), n, d, _ptr(r), m, _ptr(S), float(m_total), _ptr(out), _stream()),
+                   "vatlq_cosine_rowsum")
+    return out
+
+
+def minmax_f64(v: torch.Tensor, mask=None, group=None) -> torch.Tensor:
+    """(v - min) / (max - min) over the rows with mask != 0, 0 elsewhere, fp64 (the influence
+    normalisation of ActiveLearning.py:477); returns a new tensor."""
+    v = _cuda(v, torch.float64, "v").clone()
+    n = v.numel()
+    mk = _flags(mask, n, v.device, "mask")
+    s2 = torch.empty(2, dtype=torch.float64, device=v.device)
+    L = _lib.lib()
+    with torch.cuda.device(v.device):
+        _lib.check(L.vatlq_minmax_stats_f64(_ptr(v), _ptr(mk), n, _ptr(s2), _stream()), "vatlq_minmax_stats_f64")
+        if group is not None:
+            torch.distributed.all_reduce(s2, op=torch.distributed.ReduceOp.MIN, group=group)
+        _lib.check(L.vatlq_fuse_final(_ptr(mk), n, _ptr(s2), _ptr(v), _stream()), "vatlq_fuse_final")
+    return v
+
+
+def blend_scores(unc: torch.Tensor, infl: torch.Tensor, combine_weight: float, mask=None) -> torch.Tensor:
+    """combine_weight * unc + (1 - combine_weight) * influence (ActiveLearning.py:519), fp64."""
+    unc = _cuda(unc, torch.float64, "unc")
+    infl = _cuda(infl, torch.float64, "infl")
+    n = unc.numel()
+    if infl.numel() != n:
+        raise _lib.VatlqError("unc and infl must have the same length")
+    mk = _flags(mask, n, unc.device, "mask")
+    out = torch.empty(n, dtype=torch.float64, device=unc.device)
+    with torch.cuda.device(unc.device):
+        _lib.check(_lib.lib().vatlq_fuse_blend(_ptr(unc), _ptr(infl), _ptr(mk), n, float(combine_weight), _ptr(out), _stream()),
+                   "vatlq_fuse_blend")
+    return out

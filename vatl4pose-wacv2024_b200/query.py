@@ -32,6 +32,9 @@ class QueryResult:
     extra: dict = field(default_factory=dict)
 
 
+SINGLE_UNCERTAINTIES = ("HP", "TPC", "Entropy")   # one fp32 score per item, min-max normalised (:511-516)
+
+
 class QueryPass:
     """Device-side state of one AL query over a pool of `n_local` items on this rank."""
 
@@ -43,9 +46,11 @@ class QueryPass:
         _lib.lib()  # fail now, loudly, if the CUDA library is missing
         self.n = int(n_local)
         self.uncertainty = uncertainty
-        self.use_thc = "THC" in uncertainty
-        self.use_wpu = "WPU" in uncertainty
-        if not (self.use_thc or self.use_wpu or uncertainty == "None"):
+        # dispatch order of ActiveLearning.py:329-401: exact names first, then the substring tests
+        self.single = uncertainty if uncertainty in SINGLE_UNCERTAINTIES else None
+        self.use_thc = self.single is None and "THC" in uncertainty
+        self.use_wpu = self.single is None and "WPU" in uncertainty
+        if not (self.use_thc or self.use_wpu or self.single or uncertainty == "None"):
             raise ValueError("Uncertainty type is not supported by the accelerated path")
         self.nj, self.hm = n_joints, tuple(hm_shape)
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -54,8 +59,15 @@ class QueryPass:
         self.peak_sum = torch.zeros(self.n, **f32)
         self.peak_cnt = torch.zeros(self.n, dtype=torch.int32, device=self.dev)
         self.peak_mean = torch.zeros(self.n, **f32)
-        self.kpts = torch.zeros((self.n, n_joints, 3), **f32) if (keep_kpts or self.use_wpu) else None
-        self.coords_hm = torch.zeros((self.n, n_joints, 2), **f32) if keep_kpts else None
+        pose = self.single in ("HP", "TPC")
+        self.kpts = torch.zeros((self.n, n_joints, 3), **f32) if (keep_kpts or self.use_wpu or pose) else None
+        self.coords_hm = torch.zeros((self.n, n_joints, 2), **f32) if (keep_kpts or pose) else None
+        # HP / TPC are finished from the scan's outputs once every chunk is in; Entropy per chunk
+        self.aux = torch.zeros(self.n, **f32) if self.single else None
+        self._aux_done = self.single != "TPC" and self.single != "HP"
+        self._boxes = torch.zeros((self.n, 4), **f32) if pose else None
+        self._flags = torch.zeros((2, self.n), dtype=torch.uint8, device=self.dev) if self.single == "TPC" else None
+        self._halo_xy = [None, None]
         self._carry = None        # last frame of the previous chunk (halo_prev of the next)
         self._carry_pos = 0
         self._pending = None      # a chunk whose last frame still waits for its successor
@@ -112,6 +124,18 @@ class QueryPass:
                 self._pending = None
         self._carry = H[m - 1].clone()
         self._carry_pos = pos + m
+        if self.single == "Entropy":
+            self.aux[sl] = ops.heatmap_entropy(H)
+        if self._boxes is not None:
+            self._boxes[sl] = boxes_xyxy
+        if self._flags is not None:
+            self._flags[0, sl] = ops._flags(is_prev, m, self.dev, "is_prev")
+            self._flags[1, sl] = ops._flags(is_next, m, self.dev, "is_next")
+            # heat-map-space coordinates of the neighbouring ranks' frames (TPC across a shard boundary)
+            if first and halo_prev is not None:
+                self._halo_xy[0] = ops.heatmap_scan(halo_prev.reshape(1, *H.shape[1:])).coords_hm[0]
+            if last_chunk and halo_next is not None:
+                self._halo_xy[1] = ops.heatmap_scan(halo_next.reshape(1, *H.shape[1:])).coords_hm[0]
         if self.use_wpu:
             w, ind, z = self.ae
             self.wpu[sl] = ops.wpu(res.kpts, boxes_xyxy, w, ind, z, drop_ears=not self.use_thc)
@@ -120,6 +144,8 @@ class QueryPass:
         """Score a pool that is already resident (one scan call, or chunked when asked)."""
         self._carry = None
         self._pending = None
+        self._halo_xy = [None, None]
+        self._aux_done = self.single not in ("HP", "TPC")
         if chunk is None or chunk >= H.shape[0]:
             self.score_chunk(0, H, boxes_xyxy, is_prev, is_next, halo_prev, halo_next)
             return
@@ -128,6 +154,18 @@ class QueryPass:
             b = min(n, a + chunk)
             self.score_chunk(a, H[a:b], boxes_xyxy[a:b], is_prev[a:b], is_next[a:b],
                              halo_prev if a == 0 else None, halo_next if b == n else None)
+
+    def single_score(self) -> torch.Tensor:
+        """The per-item HP / TPC / Entropy uncertainty (fp32), finished on first use."""
+        if not self._aux_done:
+            hp, tpc = ops.pose_uncertainty(self.coords_hm, self.kpts, self._boxes,
+                                           None if self._flags is None else self._flags[0],
+                                           None if self._flags is None else self._flags[1], self.hm,
+                                           self._halo_xy[0], self._halo_xy[1],
+                                           want_hp=self.single == "HP", want_tpc=self.single == "TPC")
+            self.aux.copy_(hp if self.single == "HP" else tpc)
+            self._aux_done = True
+        return self.aux
 
     # ------------------------------------------------------------------ fusion
     def fuse(self, unlabeled_mask: torch.Tensor, thc_vs_wpu: str = "const", labeled_ratio: float = 0.0,
@@ -146,7 +184,7 @@ class QueryPass:
             return torch.zeros(self.n, dtype=torch.float64, device=self.dev)   # :490-491, :523-524
         if self.use_thc and self.use_wpu:
             return ops.fuse_scores(self.thc, self.wpu, unl, thc_vs_wpu, labeled_ratio, group=group)
-        single = self.thc if self.use_thc else self.wpu
+        single = self.single_score() if self.single else (self.thc if self.use_thc else self.wpu)
         return ops.fuse_scores(single, None, unl, "single", group=group)
 
 

@@ -58,15 +58,44 @@ def parse():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: through NVML
+    (nvidia_ml_py, one sample every 20 ms) when it loads, else `nvidia-smi` every 200 ms (the recipe's
+    clocks line; one call takes longer than a short timed region, hence NVML first)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self._nvml
+        masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                self.rows.append([str(sm), str(self._max)] + ["Active" if r & m else "Not Active" for m in masks])
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
@@ -79,7 +108,7 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
         self._t.start()
         return self
 
@@ -89,13 +118,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "source": self.source}
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [nm for k, nm in enumerate(self.NAMES) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------ CPU arm

@@ -105,7 +105,8 @@ def test_cosine_rowsum_full_width_and_zero_rows(built_lib):
     got = v.ops.cosine_rowsum(torch.from_numpy(X32).cuda()).cpu().numpy()
     assert np.allclose(got, ref, rtol=1e-10, atol=0)
     Z = torch.zeros((6, 64), device="cuda")               # the reference's all-zero fvecs_matrix (:270,283)
-    assert v.ops.cosine_rowsum(Z).cpu().tolist() == [6.0] * 6
+    assert v.ops.cosine_rowsum(Z).cpu().tolist() == [5.0] * 6                 # distance 1 to the others, 0 to itself
+    assert O.cosine_rowsum(np.zeros((6, 64))).tolist() == [5.0] * 6
 
 
 class FakeEstimator(torch.nn.Module):

@@ -3,6 +3,8 @@
 //   * heat-map Entropy as one more streaming pass                  (ActiveLearning.py:790-796)
 //   * Influence / Diversity: row sums of the cosine-distance matrix (ActiveLearning.py:467-483,581-590)
 //   * the uncertainty / representativeness blend                   (ActiveLearning.py:517-521)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vatlq {
@@ -100,11 +102,15 @@ pose_unc_kernel(const float* __restrict__ coords_hm, const float* __restrict__ k
 // One warp per (frame, joint) map: the map is read from HBM once and kept in registers between
 // the sum and the entr pass when it is a 64x48 map (24 float4 per lane).
 // ------------------------------------------------------------------------------------
+// entr(p) with the MUFU logarithm (lg2 * ln 2: relative error ~1e-7 on log p, far inside the 1e-5
+// budget).  Branch-free: tiny p (MUFU flushes denormals) are scaled by 2^64 first.
 __device__ __forceinline__ float entr_f32(float p) {
-  if (p > 0.f) return -p * logf(p);
-  if (p == 0.f) return 0.f;
-  if (p < 0.f) return -INFINITY;
-  return p;  // NaN
+  const bool tiny = p < 1e-30f;
+  const float l2 = __log2f(p * (tiny ? 18446744073709551616.f : 1.f)) - (tiny ? 64.f : 0.f);
+  float e = -p * (l2 * 0.69314718055994531f);     // p < 0: NaN here, fixed below; NaN p stays NaN
+  e = (p == 0.f) ? 0.f : e;
+  e = (p < 0.f) ? -INFINITY : e;
+  return e;
 }
 
 template <int NV>  // NV float4 per lane when the map is NV*128 pixels, 0: generic (second read from L2)
@@ -132,11 +138,17 @@ entropy_kernel(const float* __restrict__ H, int64_t maps, int npx, float* __rest
     }
     acc += (double)s;
     const float S = (float)warp_sum(acc);   // np.sum(pk) is fp32
+    // p = x / S as x * (1/S) when 1/S is a normal number (within 1 ulp of numpy's quotient), else
+    // the IEEE division (S == 0 -> inf / NaN exactly like numpy)
+    const float rS = __frcp_rn(S);
+    const bool mul = fabsf(rS) > 1e-30f && fabsf(rS) < 1e30f;
     double ea = 0.0;
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-      const float e4 = (entr_f32(__fdiv_rn(v[q].x, S)) + entr_f32(__fdiv_rn(v[q].y, S))) +
-                       (entr_f32(__fdiv_rn(v[q].z, S)) + entr_f32(__fdiv_rn(v[q].w, S)));
+      float4 p;
+      if (mul) p = make_float4(v[q].x * rS, v[q].y * rS, v[q].z * rS, v[q].w * rS);
+      else p = make_float4(__fdiv_rn(v[q].x, S), __fdiv_rn(v[q].y, S), __fdiv_rn(v[q].z, S), __fdiv_rn(v[q].w, S));
+      const float e4 = (entr_f32(p.x) + entr_f32(p.y)) + (entr_f32(p.z) + entr_f32(p.w));
       ea += (double)e4;
     }
     e = (float)warp_sum(ea);
@@ -164,7 +176,11 @@ entropy_frames_kernel(const float* __restrict__ per_map, int64_t n, int J, float
 // Influence / Diversity.  KNeighborsTransformer(mode='distance', metric='cosine',
 // n_neighbors=m-1).fit_transform(X_sub) holds every pairwise cosine distance, and the score is
 // its row sum: sum_j (1 - xh_i . xh_j) = m - xh_i . S with S = sum_j xh_j, xh = x / |x|
-// (sklearn normalize: a zero row stays zero).  O(m d) instead of O(m^2 d), two streaming
+// (sklearn normalize: a zero row stays zero; its self-distance is the zeroed diagonal, so its row
+// sum is m - 1 — for pools small enough that sklearn's pairwise_distances_chunked takes one chunk,
+// which is where `X is Y` holds; zero embeddings do not occur after ReLU + average pooling except
+// for the reference's all-zero fvecs_matrix, :270,283, where the normalised score is 0/0 either
+// way).  O(m d) instead of O(m^2 d), two streaming
 // passes over the rows, fp64 accumulation.
 //   colsum: every warp walks rows, keeps its share of S in registers (d <= 2048: 16 float4
 //           columns per lane), CTA partials land in the workspace and are added in a fixed order.
@@ -172,62 +188,73 @@ entropy_frames_kernel(const float* __restrict__ per_map, int64_t n, int J, float
 // ------------------------------------------------------------------------------------
 constexpr int kCosNV = 16;        // float4 per lane per row: d <= 2048
 constexpr int kCosThreads = 256;
+constexpr int kCosRows = kCosThreads / 32;   // rows per tile: one per warp
 
 __device__ __forceinline__ const float4* cos_row(const float* X, int d, const int64_t* rows, int64_t i) {
   const int64_t r = rows ? rows[i] : i;
   return reinterpret_cast<const float4*>(X + (size_t)r * d);
 }
 
-__global__ void __launch_bounds__(kCosThreads)
+// column sums of the normalised rows.  A CTA takes tiles of 8 rows: warp w loads row w (streamed
+// through shared memory, the squared norm reduced on the way), then every thread adds the 8
+// scaled rows into the (up to two) float4 columns it owns.  CTA partials -> workspace.
+__global__ void __launch_bounds__(kCosThreads, 2)
 cos_colsum_kernel(const float* __restrict__ X, int d, const int64_t* __restrict__ rows, int64_t m,
                   double* __restrict__ partial /* gridDim.x x d */) {
-  extern __shared__ double s_S[];   // d doubles
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  extern __shared__ __align__(16) unsigned char cos_smem[];
+  float4* s_x = reinterpret_cast<float4*>(cos_smem);   // kCosRows x d4
+  __shared__ double s_inv[kCosRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = d >> 2;
-  double acc[kCosNV][4];
-#pragma unroll
-  for (int q = 0; q < kCosNV; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * nw + warp; i < m; i += (int64_t)gridDim.x * nw) {
-    const float4* rp = cos_row(X, d, rows, i);
-    float4 v[kCosNV];
+  double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+  const int64_t tiles = (m + kCosRows - 1) / kCosRows;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t i = tile * kCosRows + warp;
     double nn = 0.0;
-#pragma unroll
-    for (int q = 0; q < kCosNV; ++q) {
-      const int c = q * 32 + lane;
-      v[q] = (c < d4) ? ldg_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      nn = fma((double)v[q].x, (double)v[q].x, nn);
-      nn = fma((double)v[q].y, (double)v[q].y, nn);
-      nn = fma((double)v[q].z, (double)v[q].z, nn);
-      nn = fma((double)v[q].w, (double)v[q].w, nn);
-    }
-    nn = warp_sum(nn);
-    const double inv = nn > 0.0 ? 1.0 / sqrt(nn) : 1.0;   // zero rows: norm treated as 1
-#pragma unroll
-    for (int q = 0; q < kCosNV; ++q) {
-      acc[q][0] = fma((double)v[q].x, inv, acc[q][0]);
-      acc[q][1] = fma((double)v[q].y, inv, acc[q][1]);
-      acc[q][2] = fma((double)v[q].z, inv, acc[q][2]);
-      acc[q][3] = fma((double)v[q].w, inv, acc[q][3]);
-    }
-  }
-  // warps add their shares into the CTA's copy one after the other (fixed order)
-  for (int turn = 0; turn < nw; ++turn) {
-    if (warp == turn) {
-#pragma unroll
+    if (i < m) {
+      const float4* rp = cos_row(X, d, rows, i);
+#pragma unroll 8
       for (int q = 0; q < kCosNV; ++q) {
         const int c = q * 32 + lane;
         if (c < d4) {
+          const float4 v = ldg_stream(rp + c);
+          s_x[warp * d4 + c] = v;
+          nn = fma((double)v.x, (double)v.x, nn);
+          nn = fma((double)v.y, (double)v.y, nn);
+          nn = fma((double)v.z, (double)v.z, nn);
+          nn = fma((double)v.w, (double)v.w, nn);
+        }
+      }
+    }
+    nn = warp_sum(nn);
+    // rows past the end scale whatever the stage holds by 0 (it holds finite leftovers or zeros)
+    if (lane == 0) s_inv[warp] = (i < m) ? (nn > 0.0 ? 1.0 / sqrt(nn) : 1.0) : 0.0;
+    __syncthreads();
+    const int nr = (int)min((int64_t)kCosRows, m - tile * kCosRows);
+    for (int r = 0; r < nr; ++r) {
+      const double inv = s_inv[r];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c * 4 + e;
-            s_S[col] = (turn == 0) ? acc[q][e] : s_S[col] + acc[q][e];
-          }
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c = threadIdx.x + hh * kCosThreads;
+        if (c < d4) {
+          const float4 v = s_x[r * d4 + c];
+          acc[hh][0] = fma((double)v.x, inv, acc[hh][0]);
+          acc[hh][1] = fma((double)v.y, inv, acc[hh][1]);
+          acc[hh][2] = fma((double)v.z, inv, acc[hh][2]);
+          acc[hh][3] = fma((double)v.w, inv, acc[hh][3]);
         }
       }
     }
     __syncthreads();
   }
-  for (int col = threadIdx.x; col < d; col += blockDim.x) partial[(size_t)blockIdx.x * d + col] = s_S[col];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int c = threadIdx.x + hh * kCosThreads;
+    if (c < d4) {
+      double* o = partial + (size_t)blockIdx.x * d + (size_t)c * 4;
+      o[0] = acc[hh][0]; o[1] = acc[hh][1]; o[2] = acc[hh][2]; o[3] = acc[hh][3];
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -239,37 +266,49 @@ cos_colsum_reduce_kernel(const double* __restrict__ partial, int parts, int d, d
   S[col] = s;
 }
 
+// out_i = m_total - (x_i . S) / |x_i|: one warp per row, S in shared memory
 __global__ void __launch_bounds__(kCosThreads)
 cos_rowsum_kernel(const float* __restrict__ X, int d, const int64_t* __restrict__ rows, int64_t m,
                   const double* __restrict__ S, double m_total, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char cos_smem[];
+  double* s_S = reinterpret_cast<double*>(cos_smem);   // d doubles
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int d4 = d >> 2;
-  double s[kCosNV][4];
-#pragma unroll
-  for (int q = 0; q < kCosNV; ++q) {
-    const int c = q * 32 + lane;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) s[q][e] = (c < d4) ? S[c * 4 + e] : 0.0;
-  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s_S[c] = S[c];
+  __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * nw + warp; i < m; i += (int64_t)gridDim.x * nw) {
     const float4* rp = cos_row(X, d, rows, i);
     double nn = 0.0, dot = 0.0;
 #pragma unroll
-    for (int q = 0; q < kCosNV; ++q) {
-      const int c = q * 32 + lane;
-      const float4 v = (c < d4) ? ldg_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      nn = fma((double)v.x, (double)v.x, nn);
-      nn = fma((double)v.y, (double)v.y, nn);
-      nn = fma((double)v.z, (double)v.z, nn);
-      nn = fma((double)v.w, (double)v.w, nn);
-      dot = fma((double)v.x, s[q][0], dot);
-      dot = fma((double)v.y, s[q][1], dot);
-      dot = fma((double)v.z, s[q][2], dot);
-      dot = fma((double)v.w, s[q][3], dot);
+    for (int q0 = 0; q0 < kCosNV; q0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = (q0 + q) * 32 + lane;
+        v[q] = (c < d4) ? ldg_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = (q0 + q) * 32 + lane;
+        if (c < d4) {
+          const double2 sa = *reinterpret_cast<const double2*>(s_S + (size_t)c * 4);
+          const double2 sb = *reinterpret_cast<const double2*>(s_S + (size_t)c * 4 + 2);
+          nn = fma((double)v[q].x, (double)v[q].x, nn);
+          nn = fma((double)v[q].y, (double)v[q].y, nn);
+          nn = fma((double)v[q].z, (double)v[q].z, nn);
+          nn = fma((double)v[q].w, (double)v[q].w, nn);
+          dot = fma((double)v[q].x, sa.x, dot);
+          dot = fma((double)v[q].y, sa.y, dot);
+          dot = fma((double)v[q].z, sb.x, dot);
+          dot = fma((double)v[q].w, sb.y, dot);
+        }
+      }
     }
     nn = warp_sum(nn);
     dot = warp_sum(dot);
-    if (lane == 0) out[i] = m_total - (nn > 0.0 ? dot / sqrt(nn) : dot);
+    // a zero row has cosine distance 1 to every other row and 0 to itself (sklearn zeroes the
+    // diagonal when the graph is built over the fitted rows themselves): m_total - 1
+    if (lane == 0) out[i] = nn > 0.0 ? m_total - dot / sqrt(nn) : m_total - 1.0;
   }
 }
 
@@ -394,7 +433,13 @@ extern "C" int vatlq_cosine_colsum(const float* X, int64_t n, int d, const int64
     return 0;
   }
   const int grid = cos_grid(m);
-  cos_colsum_kernel<<<grid, kCosThreads, (size_t)d * sizeof(double), stream>>>(X, d, rows, m, (double*)ws);
+  const size_t smem = (size_t)kCosRows * d * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    VQ_CUDA(cudaFuncSetAttribute(cos_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCosRows * kCosNV * 128 * 4));
+    cfg = true;
+  }
+  cos_colsum_kernel<<<grid, kCosThreads, smem, stream>>>(X, d, rows, m, (double*)ws);
   VQ_LAUNCHED();
   cos_colsum_reduce_kernel<<<(d + 255) / 256, 256, 0, stream>>>((const double*)ws, grid, d, S);
   VQ_LAUNCHED();
@@ -409,7 +454,8 @@ extern "C" int vatlq_cosine_rowsum(const float* X, int64_t n, int d, const int64
   VQ_REQUIRE(((uintptr_t)X & 15) == 0, "X must be 16-byte aligned");
   VQ_REQUIRE(rows != nullptr || m == n, "m must equal n without a row list");
   if (m == 0) return 0;
-  cos_rowsum_kernel<<<cos_grid(m), kCosThreads, 0, stream>>>(X, d, rows, m, S, m_total, out);
+  const int grid = (int)std::min<int64_t>((m + kCosRows - 1) / kCosRows, (int64_t)sm_count() * 6);
+  cos_rowsum_kernel<<<grid, kCosThreads, (size_t)d * sizeof(double), stream>>>(X, d, rows, m, S, m_total, out);
   VQ_LAUNCHED();
   return 0;
 }

@@ -49,6 +49,7 @@ def parse():
                    help="core-set picks per round (1 = GEMV form, 8 = one pass per round, 16 = two passes per round); "
                         "default 8, and 16 from 4 GPUs on where the fixed cost of a round outweighs the pass")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-prune", action="store_true", help="core-set passes stream every tile (exact pruning off)")
     p.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather per round instead of the peer-memory mailbox")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-frames", type=int, default=512, help="frames of the CPU scoring sample")
@@ -190,6 +191,7 @@ def main():
     config = {"workload": workload, "frames": n, "k": k, "feat_dim": D, "labelled": n_lab, "moks": moks,
               "unc_lambda": lam, "coreset_batch": a.batch, "parallelism": f"frame-range sharding x{world}",
               "candidate_exchange": "none" if world == 1 else ("ncclAllGather" if a.no_p2p else "peer-memory mailbox (NVLink stores + flags)"),
+              "coreset_pruning": "off" if a.no_prune else "exact (segments of consecutive rows + triangle inequality; picks unchanged)",
               "l2": "inputs (>= 4 GB of heat maps + >= 174 MB of features per rank) exceed the 126 MB L2"}
 
     if a.impl == "reference":
@@ -240,6 +242,8 @@ def main():
     comm = vd.Comm(use_p2p=not a.no_p2p) if world > 1 else None
     lib = vatlq._lib.lib()
     lib.vatlq_profile_passes(1)
+    if a.no_prune:
+        ops.set_prune("off")
 
     def step_resident():
         if world == 1:
@@ -257,6 +261,7 @@ def main():
     barrier()
     import ctypes as C
     lib.vatlq_profile_read(None, None, None, 1)
+    ops.prune_stats(reset=True)
     launches0 = vatlq._lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -274,6 +279,8 @@ def main():
     tot_ms, n_pass, n_picks = C.c_double(), C.c_int64(), C.c_int64()
     lib.vatlq_profile_read(C.byref(tot_ms), C.byref(n_pass), C.byref(n_picks), 1)
     lib.vatlq_profile_passes(0)
+    prune = ops.prune_stats(reset=True)
+    streamed_frac = prune["streamed"] / prune["tiles"] if prune["tiles"] else 1.0
     st = res.stats
     picks_ref = res.picks.clone()
 
@@ -286,8 +293,9 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     per_step_bytes = nl * D * 4 + 16 * nl            # one greedy step over the owned rows
-    # what ONE pass must move: X once + xx r, min_d r/w, unc r/w, score w (fp64 each)  
-    per_pass_bytes = nl * D * 4 + 40 * nl
+    # what ONE pass must move: the rows of X it streams (all of them without pruning; the pruned tiles are
+    # provably unaffected and never read) + xx r, min_d r/w, unc r/w, score w (fp64 each)  
+    per_pass_bytes = nl * D * 4 * streamed_frac + 40 * nl
     roof = None
     if n_pass.value > 0 and tot_ms.value > 0:
         picks_per_launch = n_picks.value / n_pass.value
@@ -295,9 +303,10 @@ def main():
         achieved = per_pass_bytes / avg_s / 1e9
         roof = {"kernel": "pass_kernel_tma (core-set distance update: TMA-staged tiles, fp64 tensor-core DMMA, row finishing)", "bound": "hbm",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": ncu_traffic("pass_kernel", nl),
+                "traffic": ncu_traffic("pass_kernel" if a.no_prune else "pass_kernel_pruned", nl),
                 "peak_source": peak_src, "avg_launch_us": avg_s * 1e6, "launches_timed": n_pass.value,
-                "algorithmic_bytes_per_launch": per_pass_bytes,
+                "algorithmic_bytes_per_launch": per_pass_bytes, "streamed_fraction_of_X": streamed_frac,
+                "unpruned_bytes_per_launch": nl * D * 4 + 40 * nl, "segments": prune["segments"],
                 "greedy_steps_per_launch": picks_per_launch, "algorithmic_bytes_per_greedy_step": per_step_bytes,
                 "greedy_equivalent_gbs": picks_per_launch * per_step_bytes / avg_s / 1e9,
                 "fp64_fma_per_s": picks_per_launch * nl * D / avg_s,

@@ -150,6 +150,19 @@ int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64
                          int64_t* out_idx, void* comm,
                          void* ws, size_t ws_bytes, int64_t* host_stats, vatlq_stream_t stream);
 
+/* Exact pruning of the passes over X (d == 2048, >= VATLQ_PRUNE_MIN_ROWS owned rows, default 8192):
+ * consecutive rows of an id-sorted pool are near each other, so the owned rows are cut into segments
+ * with an anchor row and a radius, and a pass does not stream the 8-row tiles whose segments
+ * provably (triangle inequality, with a margin far above the fp64 rounding) cannot get closer to
+ * any of the pass's centres.  The pick list is unchanged.  Environment: VATLQ_PRUNE=0 disables,
+ * VATLQ_PRUNE=verify streams everything and counts rows of flagged tiles whose min_d moved.
+ * host_out4 = {tiles seen, tiles streamed, verify violations (must be 0), segments of the last
+ * call}, accumulated over the vatlq_coreset_select calls since the last reset. */
+int vatlq_coreset_prune_stats(int64_t* host_out4, int reset);
+/* process-wide override of the two environment settings: mode -1 environment, 0 off, 1 prune,
+ * 2 verify; min_rows < 0: environment */
+int vatlq_coreset_set_prune(int mode, int64_t min_rows);
+
 /* One pairwise-distance column block, exposed for parity tests of the distance arithmetic:
  * out[i*m + j] = d(X[i], X[centers[j]]) in fp64 (sklearn _euclidean_distances order). */
 int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,

@@ -16,5 +16,7 @@ def test_two_gpus_match_one(built_lib):
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    # prune even these small shards so that the segment / tile bookkeeping is exercised with row offsets
+    env = dict(os.environ, VATLQ_PRUNE_MIN_ROWS="0")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -330,6 +330,12 @@ struct PassArgs {
   PushArgs push;             // push.peers != null: the published block is pushed to every rank's mailbox
   unsigned char* did_work;   // optional: set to 1 when this launch applied centres (pass timing bookkeeping)
   double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
+  // exact pruning (fast path only, see "pruning" below): tiles whose segments were all flagged by
+  // prune_filter_kernel are not streamed; their rows keep min_d and only take part in the epilogue
+  const int* seg_of_row;             // [owned row] -> segment id, or null
+  const unsigned char* seg_skip;     // [segment] 1: no row of the segment can get closer to this pass's centres
+  int prune_mode;                    // 0 off, 1 skip, 2 verify (stream everything, count rows that changed anyway)
+  unsigned long long* prune_stats;   // [0] tiles seen, [1] tiles streamed, [2] verify violations
 };
 
 // centres of THIS pass: count (<= 0: nothing to do) and whether it is the round's last pass
@@ -621,21 +627,27 @@ __device__ __forceinline__ ApplyConst apply_const(const PassArgs& a, bool final_
   }
   return c;
 }
+// tile_mode: 0 streamed, 1 pruned (no dot products were computed: min_d stays), 2 verify (streamed
+// although the filter flagged it: count the rows whose min_d moved anyway — must stay 0)
 __device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c, long long i, const double* s_xxc,
-                                          const long long* s_pick, unsigned int* s_hist, Best& best) {
+                                          const long long* s_pick, unsigned int* s_hist, Best& best, int tile_mode = 0) {
   const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
   const double xxi = a.xx[i];
   double tm = INFINITY;
   bool picked = false;
+  if (tile_mode != 1) {
 #pragma unroll
-  for (int q = 0; q < kB / 2; ++q) {
-    const double2 d2 = __ldcg(dp + q);
-    tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
-    tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
-    picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
+    for (int q = 0; q < kB / 2; ++q) {
+      const double2 d2 = __ldcg(dp + q);
+      tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
+      tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
+      picked = picked || s_pick[2 * q] == i || s_pick[2 * q + 1] == i;
+    }
   }
-  const double dmin = fmin(a.m[i], sqrt(fmax(tm, 0.0)));
-  a.m[i] = dmin;
+  const double m_old = a.m[i];
+  const double dmin = fmin(m_old, sqrt(fmax(tm, 0.0)));
+  if (tile_mode == 2 && (dmin != m_old || picked)) atomicAdd(&a.prune_stats[2], 1ULL);
+  if (tile_mode != 1) a.m[i] = dmin;
   if (a.unc) {
     double u = a.unc[i];
     if (picked) {
@@ -678,8 +690,9 @@ constexpr int kPartBufs = 3;
 constexpr int kRowBytesX = 2048 * 4 + 64;                  // stage row stride
 constexpr int kStageBytesX = 8 * kRowBytesX;               // 66 048
 constexpr int kWsThreads = (kSeg + 4) * 32;                // 8 compute warps + producer + 3 epilogue warps
+constexpr int kMaxTilesCta = 2048;                         // tiles per CTA the pruned-tile list can hold
 constexpr size_t kWsSmem = (size_t)kStagesX * kStageBytesX + sizeof(double) * kPartBufs * kSeg * 64 + 2 * kStagesX * 8 +
-                           kB * 16 + (kNB + 1) * 4 + 128;
+                           kB * 16 + (kNB + 1) * 4 + 128 + kMaxTilesCta * 2 + kMaxTilesCta / 8 + 16;
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void named_sync(int id, int count) {
@@ -705,6 +718,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   double* s_xxc = reinterpret_cast<double*>(empty + kStagesX);
   long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
   unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
+  // pruning: the tiles this CTA streams (indices k into its own tile sequence), a bitmap of the
+  // flagged ones, and the number of streamed tiles
+  unsigned short* s_tiles = reinterpret_cast<unsigned short*>(s_hist + (kNB + 1) + 3);
+  unsigned int* s_flagged = reinterpret_cast<unsigned int*>(s_tiles + kMaxTilesCta);
+  int* s_na = reinterpret_cast<int*>(s_flagged + kMaxTilesCta / 32);
 
   bool final_pass;
   const int nb = pass_centers(a, final_pass);
@@ -728,10 +746,44 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-
   const long long ntiles = (a.hi - a.lo + 7) / 8;
   const int nt = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  // tile j of the streamed sequence is tile k = tile_of(j) of the CTA (rows (blockIdx.x + k*gridDim.x)*8 ...)
+  const bool use_list = a.seg_skip != nullptr && a.prune_mode != 0 && nt <= kMaxTilesCta;
+  if (warp == kSeg + 1) {
+    int na = 0;
+    if (use_list) {
+      for (int base = 0; base < nt; base += 32) {
+        const int k = base + lane;
+        bool flagged = false;
+        if (k < nt) {
+          const long long r0 = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8;   // relative to a.lo
+          const long long r1 = min(r0 + 7, a.hi - a.lo - 1);
+          const int s0 = a.seg_of_row[r0], s1 = a.seg_of_row[r1];
+          flagged = true;
+          for (int sg = s0; sg <= s1; ++sg) flagged = flagged && (a.seg_skip[sg] != 0);
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, flagged);
+        if (lane == 0) s_flagged[base >> 5] = fm;
+        const bool stream = (k < nt) && !(flagged && a.prune_mode == 1);
+        const unsigned sm = __ballot_sync(0xffffffffu, stream);
+        if (stream) s_tiles[na + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)k;
+        na += __popc(sm);
+      }
+    } else {
+      na = nt;
+    }
+    if (lane == 0) {
+      *s_na = na;
+      if (a.prune_stats && nt > 0) {
+        atomicAdd(&a.prune_stats[0], (unsigned long long)nt);
+        atomicAdd(&a.prune_stats[1], (unsigned long long)na);
+      }
+    }
+  }
+  __syncthreads();
+  const int na = *s_na;
+  auto tile_of = [&](int j) -> int { return use_list ? (int)s_tiles[j] : j; };
 
   if (warp < kSeg) {
     // ------------------------------------------------------------------ compute warps
@@ -754,7 +806,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     const unsigned my_part = smem_addr(&s_part[0][seg][lane * 2]);
     int st = 0, pb = 0;
     unsigned phase = 0;
-    for (int k = 0; k < nt; ++k) {
+    for (int k = 0; k < na; ++k) {
       mbar_wait(&full[st], phase);
       const unsigned ap = a_off + st * kStageBytesX;
       double c[4][2];
@@ -790,8 +842,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
       // lane r < 8 copies row r of every tile; rows past the end re-read the last row
       int st = 0;
       unsigned phase = 0;
-      for (int k = 0; k < nt; ++k) {
-        if (k >= kStagesX) mbar_wait(&empty[st], phase ^ 1u);   // the stage's previous tile was released
+      for (int j = 0; j < na; ++j) {
+        const int k = tile_of(j);
+        if (j >= kStagesX) mbar_wait(&empty[st], phase ^ 1u);   // the stage's previous tile was released
         if (lane == 0) mbar_expect_tx(&full[st], 8u * 2048u * 4u);
         __syncwarp();
         if (lane < 8) {
@@ -807,11 +860,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
       // ---------------------------------------------------------------- epilogue warps
       const int ew = warp - kSeg - 1;             // partial buffer of this warp: tiles k = ew, ew+3, ...
       const int r = lane >> 2;                    // lane (r,kk): row r, centres 2kk, 2kk+1 (the DMMA C layout)
-      for (int k = ew; k < nt; k += kPartBufs) {
+      for (int j = ew; j < na; j += kPartBufs) {
+        const int k = tile_of(j);
         named_sync(1 + ew, kSeg * 32 + 32);
         const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
         const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
-        if (k + kPartBufs < nt) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
+        if (j + kPartBufs < na) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
         const long long row = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + r;   // relative to a.lo
         if (a.lo + row < a.hi) *reinterpret_cast<double2*>(a.dots + row * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
       }
@@ -824,12 +878,203 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   const ApplyConst ac = apply_const(a, final_pass);
   if (warp < kSeg) {
     for (int q = threadIdx.x; q < nt * 8; q += kSeg * 32) {
-      const long long i = a.lo + ((long long)blockIdx.x + (long long)(q >> 3) * gridDim.x) * 8 + (q & 7);
-      if (i < a.hi) apply_row(a, ac, i, s_xxc, s_pick, s_hist, best);
+      const int k = q >> 3;
+      const long long i = a.lo + ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + (q & 7);
+      const int tile_mode = (use_list && ((s_flagged[k >> 5] >> (k & 31)) & 1u)) ? a.prune_mode : 0;
+      if (i < a.hi) apply_row(a, ac, i, s_xxc, s_pick, s_hist, best, tile_mode);
     }
   }
   __syncthreads();
   publish_pass(a, best, ac.do_hist, s_hist, final_pass);
+}
+
+// ---------------------------------------------------------------- pruning (exact)
+// Pools are id-sorted video tracks, so consecutive rows of X are near each other.  The owned rows
+// are cut into SEGMENTS (a new one wherever the distance between consecutive rows exceeds twice
+// its mean, and at least every kSegMax rows); segment s has an anchor row a_s (its first) and a
+// radius R_s = max_i d(a_s, i).  For a new centre c the triangle inequality gives, for every
+// row i of the segment,  d(i,c) >= d(a_s,c) - R_s,  so when
+//     min_j d(a_s, c_j) - R_s  >=  max_{i in s} min_d[i] + margin
+// no row of the segment can get closer to any centre c_j of this pass: min(min_d, d) leaves every
+// min_d untouched and the rows need not be streamed.  `margin` (1e-6 x the norms involved) is
+// orders of magnitude above the rounding of the canonical fp64 distances (<= ~5e-7 at d -> 0), so
+// the pruned pass writes exactly the bits the full pass would: the pick list cannot change.  A
+// picked row is never pruned (its own segment has d(a_s,c) <= R_s).  VATLQ_PRUNE=verify streams
+// everything and counts rows of flagged tiles whose min_d moved (tests assert 0).
+constexpr int kSegMax = 64;
+struct PruneCtl {
+  double sum;                      // sum of the finite consecutive-row distances
+  unsigned long long cnt;
+  int nseg, pad;
+  unsigned long long stats[3];     // tiles seen, tiles streamed, verify violations (PassArgs::prune_stats)
+};
+
+// squared distance of two rows as sum((x-y)^2) in fp64 (every lane returns the warp total)
+__device__ __forceinline__ double warp_sqdist(const float4* __restrict__ x, const float4* __restrict__ y, int d4, int lane) {
+  double acc = 0.0;
+  for (int c = lane; c < d4; c += 32) {
+    const float4 u = __ldg(x + c), v = __ldg(y + c);
+    const double a0 = (double)u.x - (double)v.x, a1 = (double)u.y - (double)v.y;
+    const double a2 = (double)u.z - (double)v.z, a3 = (double)u.w - (double)v.w;
+    acc = fma(a0, a0, acc);
+    acc = fma(a1, a1, acc);
+    acc = fma(a2, a2, acc);
+    acc = fma(a3, a3, acc);
+  }
+  return warp_sum(acc);
+}
+
+// cd[r] = d(row lo+r-1, row lo+r) for r >= 1 (cd[0] = +inf), and their sum / count
+__global__ void __launch_bounds__(256) consec_kernel(const float* __restrict__ X, int d4, long long lo, long long hi,
+                                                     double* __restrict__ cd, PruneCtl* pc) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  double local = 0.0;
+  unsigned long long cnt = 0;
+  for (long long r = w0; r < hi - lo; r += nwarps) {
+    double dist = INFINITY;
+    if (r > 0) {
+      dist = sqrt(warp_sqdist(X4 + (size_t)(lo + r) * d4, X4 + (size_t)(lo + r - 1) * d4, d4, lane));
+      if (isfinite(dist)) {
+        local += dist;
+        cnt += 1;
+      }
+    }
+    if (lane == 0) cd[r] = dist;
+  }
+  if (lane == 0 && cnt) {
+    atomicAdd(&pc->sum, local);
+    atomicAdd(&pc->cnt, cnt);
+  }
+}
+
+// one CTA: segment ids from the cuts (cd > 2 x mean, or kSegMax rows since the last cut)
+__global__ void __launch_bounds__(1024) segment_kernel(const double* __restrict__ cd, int n, PruneCtl* pc,
+                                                       int* __restrict__ seg_of_row, int* __restrict__ seg_start) {
+  __shared__ int s_a[1024], s_b[1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int per = (n + T - 1) / T;
+  const int r0 = min(n, t * per), r1 = min(n, r0 + per);
+  const double tau = pc->cnt ? 2.0 * pc->sum / (double)pc->cnt : INFINITY;
+  int last = -1;
+  for (int i = r0; i < r1; ++i)
+    if (i == 0 || cd[i] > tau) last = i;
+  s_a[t] = last;
+  __syncthreads();
+  for (int off = 1; off < T; off <<= 1) {   // inclusive max-scan: last threshold cut at or before the chunk
+    const int v = (t >= off) ? s_a[t - off] : -1;
+    __syncthreads();
+    s_a[t] = max(s_a[t], v);
+    __syncthreads();
+  }
+  const int run_in = (t > 0) ? s_a[t - 1] : -1;
+  int cnt = 0, rs = run_in;
+  for (int i = r0; i < r1; ++i) {
+    bool cut = (i == 0 || cd[i] > tau);
+    if (cut) rs = i;
+    else cut = ((i - rs) % kSegMax) == 0;
+    cnt += cut ? 1 : 0;
+  }
+  s_b[t] = cnt;
+  __syncthreads();
+  for (int off = 1; off < T; off <<= 1) {   // inclusive sum-scan of the cut counts
+    const int v = (t >= off) ? s_b[t - off] : 0;
+    __syncthreads();
+    s_b[t] += v;
+    __syncthreads();
+  }
+  int id = ((t > 0) ? s_b[t - 1] : 0) - 1;
+  rs = run_in;
+  for (int i = r0; i < r1; ++i) {
+    bool cut = (i == 0 || cd[i] > tau);
+    if (cut) rs = i;
+    else cut = ((i - rs) % kSegMax) == 0;
+    if (cut) {
+      ++id;
+      seg_start[id] = i;
+    }
+    seg_of_row[i] = id;
+  }
+  if (t == T - 1) {
+    pc->nseg = s_b[T - 1];
+    seg_start[s_b[T - 1]] = n;
+  }
+}
+
+// R_s = max_i d(anchor_s, i): one warp per segment
+__global__ void __launch_bounds__(256) seg_radius_kernel(const float* __restrict__ X, int d4, long long lo,
+                                                         const int* __restrict__ seg_start, const PruneCtl* pc,
+                                                         double* __restrict__ segR) {
+  const int lane = threadIdx.x & 31;
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const int nseg = pc->nseg;
+  for (int sg = w0; sg < nseg; sg += nwarps) {
+    const int a = seg_start[sg], e = seg_start[sg + 1];
+    double R = 0.0;
+    for (int r = a + 1; r < e; ++r)
+      R = fmax(R, sqrt(warp_sqdist(X4 + (size_t)(lo + r) * d4, X4 + (size_t)(lo + a) * d4, d4, lane)));
+    if (lane == 0) segR[sg] = R;
+  }
+}
+
+// per pass: seg_skip[s] = 1 when no row of segment s can get closer to this pass's centres
+__global__ void __launch_bounds__(256) prune_filter_kernel(const float* __restrict__ X, int d4, long long lo,
+                                                           const int* __restrict__ seg_start, const double* __restrict__ segR,
+                                                           const double* __restrict__ m, const double* __restrict__ xx,
+                                                           const Ctl* ctl, int center_off, const PruneCtl* pc,
+                                                           unsigned char* __restrict__ seg_skip) {
+  const int total = ctl->nb;
+  const int nb = min(kB, total - center_off);
+  if (nb <= 0) return;
+  __shared__ long long s_c[kB];
+  __shared__ double s_cn;
+  if (threadIdx.x < kB) s_c[threadIdx.x] = ctl->picks[center_off + min((int)threadIdx.x, nb - 1)];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = 0.0;
+    for (int j = 0; j < kB; ++j) mx = fmax(mx, xx[s_c[j]]);
+    s_cn = sqrt(mx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const int nseg = pc->nseg;
+  for (int sg = w0; sg < nseg; sg += nwarps) {
+    const int a = seg_start[sg], e = seg_start[sg + 1];
+    double M = 0.0;
+    for (int r = a + lane; r < e; r += 32) M = fmax(M, m[lo + r]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+    unsigned char skip = 0;
+    if (isfinite(M)) {
+      const float4* ap = X4 + (size_t)(lo + a) * d4;
+      double acc[kB];
+#pragma unroll
+      for (int j = 0; j < kB; ++j) acc[j] = 0.0;
+      for (int c = lane; c < d4; c += 32) {
+        const float4 u = __ldg(ap + c);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+          const float4 v = __ldg(X4 + (size_t)s_c[j] * d4 + c);
+          const double a0 = (double)u.x - (double)v.x, a1 = (double)u.y - (double)v.y;
+          const double a2 = (double)u.z - (double)v.z, a3 = (double)u.w - (double)v.w;
+          acc[j] = fma(a0, a0, acc[j]);
+          acc[j] = fma(a1, a1, acc[j]);
+          acc[j] = fma(a2, a2, acc[j]);
+          acc[j] = fma(a3, a3, acc[j]);
+        }
+      }
+      double d2min = INFINITY;
+#pragma unroll
+      for (int j = 0; j < kB; ++j) d2min = fmin(d2min, warp_sum(acc[j]));
+      const double margin = 1e-6 * (1.0 + sqrt(xx[lo + a]) + s_cn);
+      skip = (sqrt(d2min) - segR[sg] - M >= margin) ? 1 : 0;
+    }
+    if (lane == 0) seg_skip[sg] = skip;
+  }
 }
 
 static size_t pass_smem_bytes(int S) {
@@ -1442,6 +1687,7 @@ struct Comm {
 // ---------------------------------------------------------------- workspace layout
 struct WsLayout {
   size_t xx, score, hist, partial, send, recv, dcc, ctl, dots, flags, total;
+  size_t prune, seg_of_row, seg_start, seg_r, seg_skip;   // pruning state (cd aliases dots during set-up)
 };
 static WsLayout ws_layout(long long n, int world) {
   WsLayout L;
@@ -1461,6 +1707,11 @@ static WsLayout ws_layout(long long n, int world) {
   L.dcc = take((size_t)kCap * kCap * 8);
   L.dots = take((size_t)n * kB * 8);
   L.flags = take(1024);
+  L.prune = take(sizeof(PruneCtl));
+  L.seg_of_row = take((size_t)n * 4);
+  L.seg_start = take((size_t)(n + 1) * 4);
+  L.seg_r = take((size_t)n * 8);
+  L.seg_skip = take((size_t)n);
   L.total = o;
   return L;
 }
@@ -1475,6 +1726,9 @@ struct PassProfiler {
   long long picks = 0;           // picks those passes applied
 };
 static PassProfiler g_prof;
+static long long g_prune[4] = {0, 0, 0, 0};   // tiles seen, tiles streamed, verify violations, segments (last call)
+static int g_prune_mode_set = -1;              // vatlq_coreset_set_prune: -1 = take VATLQ_PRUNE
+static long long g_prune_min_set = -1;         //                          -1 = take VATLQ_PRUNE_MIN_ROWS
 
 }  // namespace vatlq
 
@@ -1631,6 +1885,35 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   if (int e = launch_norms(X, n, d, xx, stream)) return e;
 
   const int own = (int)std::min<int64_t>(row_hi - row_lo, 1LL << 30);
+  // ---- exact pruning set-up (fast path only): segments of near-consecutive rows, anchors, radii
+  static const int prune_env = []() {
+    const char* e = getenv("VATLQ_PRUNE");
+    if (!e) return 1;
+    if (!strcmp(e, "0") || !strcmp(e, "off")) return 0;
+    return !strcmp(e, "verify") ? 2 : 1;
+  }();
+  static const long long prune_min_rows = []() {
+    const char* e = getenv("VATLQ_PRUNE_MIN_ROWS");
+    return e ? atoll(e) : 8192LL;
+  }();
+  PruneCtl* pc = (PruneCtl*)(w + L.prune);
+  int* seg_of_row = (int*)(w + L.seg_of_row);
+  int* seg_start = (int*)(w + L.seg_start);
+  double* seg_r = (double*)(w + L.seg_r);
+  unsigned char* seg_skip = (unsigned char*)(w + L.seg_skip);
+  const long long prune_min = g_prune_min_set >= 0 ? g_prune_min_set : prune_min_rows;
+  const int prune_mode = (G.d4 == kSeg * 4 * 16 && row_hi - row_lo >= prune_min && row_hi - row_lo >= 8 && row_hi - row_lo < (1LL << 30))
+                             ? (g_prune_mode_set >= 0 ? g_prune_mode_set : prune_env) : 0;
+  VQ_CUDA(cudaMemsetAsync(pc, 0, sizeof(PruneCtl), stream));
+  if (prune_mode) {
+    double* cd = (double*)(w + L.dots);   // the dot-product scratch is idle until the first pass
+    consec_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, row_hi, cd, pc);
+    VQ_LAUNCHED();
+    segment_kernel<<<1, 1024, 0, stream>>>(cd, own, pc, seg_of_row, seg_start);
+    VQ_LAUNCHED();
+    seg_radius_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, seg_start, pc, seg_r);
+    VQ_LAUNCHED();
+  }
   int fgrid = std::max(1, std::min(sm_count() * 4, (own + 255) / 256));
   VQ_REQUIRE(fgrid <= 4096 && sm_count() <= 4096, "grid too large for the arg-max scratch");
   const size_t pairs_smem = G.smem;
@@ -1644,6 +1927,10 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.n_centers_imm = 0; a.ctl = ctl;
     a.hist = (nbk > 1) ? hist : nullptr; a.send = send; a.partial = partial; a.dots = (double*)(w + L.dots);
+    a.prune_stats = pc->stats;
+    if (prune_mode) {
+      a.seg_of_row = seg_of_row; a.seg_skip = seg_skip; a.prune_mode = prune_mode;
+    }
   };
 
   if (n_labeled == 0 && rule == 2) {
@@ -1655,6 +1942,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     PassArgs a{};
     fill_pass(a);
     a.send = nullptr;   // the bootstrap below computes the arg-max of the scores this pass writes
+    a.seg_skip = nullptr; a.prune_mode = 0;
     if (int e = launch_pass(a, stream)) return e;
   } else {
     const long long cnt = row_hi - row_lo;
@@ -1719,6 +2007,11 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         fill_pass(a);
         a.center_off = off;
         a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
+        if (prune_mode) {
+          prune_filter_kernel<<<sm_count() * 4, 256, 0, stream>>>(X, G.d4, row_lo, seg_start, seg_r, min_d, xx, ctl, off, pc,
+                                                                 seg_skip);
+          g_launches.fetch_add(1);
+        }
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
         rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
@@ -1768,6 +2061,15 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       rc = VATLQ_ECOMM;
     }
   }
+  if (rc == 0) {
+    PruneCtl hp{};
+    if (cudaMemcpy(&hp, pc, sizeof(PruneCtl), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      g_prune[0] += (long long)hp.stats[0];
+      g_prune[1] += (long long)hp.stats[1];
+      g_prune[2] += (long long)hp.stats[2];
+      g_prune[3] = hp.nseg;
+    }
+  }
   if (rc == 0 && host_stats) {
     const Ctl* hc = (const Ctl*)h_picked;
     host_stats[0] = hc->stat_passes;
@@ -1781,6 +2083,20 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   }
   cudaFreeHost(h_picked);
   return rc;
+}
+
+extern "C" int vatlq_coreset_set_prune(int mode, int64_t min_rows) {
+  VQ_REQUIRE(mode >= -1 && mode <= 2, "mode must be -1 (environment), 0 (off), 1 (prune) or 2 (verify)");
+  g_prune_mode_set = mode;
+  g_prune_min_set = min_rows < 0 ? -1 : (long long)min_rows;
+  return 0;
+}
+
+extern "C" int vatlq_coreset_prune_stats(int64_t* host_out4, int reset) {
+  if (host_out4)
+    for (int i = 0; i < 4; ++i) host_out4[i] = g_prune[i];
+  if (reset) g_prune[0] = g_prune[1] = g_prune[2] = g_prune[3] = 0;
+  return 0;
 }
 
 extern "C" int vatlq_pairwise_dist(const float* X, int64_t n, int d, const int64_t* centers, int64_t m,

@@ -244,6 +244,22 @@ def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: fl
     return picks, st
 
 
+PRUNE_MODES = {"env": -1, "off": 0, "on": 1, "verify": 2}
+
+
+def set_prune(mode: str = "env", min_rows: int = -1):
+    """Exact pruning of the core-set passes (include/vatlq.h): "env" (VATLQ_PRUNE), "off", "on" or
+    "verify"; min_rows < 0 keeps VATLQ_PRUNE_MIN_ROWS (default 8192 owned rows)."""
+    _lib.check(_lib.lib().vatlq_coreset_set_prune(PRUNE_MODES[mode], int(min_rows)), "vatlq_coreset_set_prune")
+
+
+def prune_stats(reset: bool = False) -> dict:
+    """Tiles seen / streamed by the passes, verify violations and the segment count of the last call."""
+    out = (C.c_int64 * 4)()
+    _lib.check(_lib.lib().vatlq_coreset_prune_stats(C.cast(out, C.c_void_p), int(reset)), "vatlq_coreset_prune_stats")
+    return {"tiles": int(out[0]), "streamed": int(out[1]), "violations": int(out[2]), "segments": int(out[3])}
+
+
 def pairwise_dist(X: torch.Tensor, centers) -> torch.Tensor:
     """(n,m) fp64 Euclidean distances of every row to X[centers] with the library's canonical
     fp64 arithmetic (sklearn order: sqrt(max(0, -2 x.c + |x|^2 + |c|^2)))."""

@@ -46,8 +46,7 @@ def parse():
     p.add_argument("--labeled-frac", type=float, default=0.0, help="already-labelled fraction (0 = round 0)")
     p.add_argument("--moks", type=float, default=None, help="mean OKS of the last queries (default 0 at round 0, else 0.6)")
     p.add_argument("--batch", type=int, default=None,
-                   help="core-set picks per round (1 = GEMV form, 8 = one pass per round, 16 = two passes per round); "
-                        "default 8, and 16 from 4 GPUs on where the fixed cost of a round outweighs the pass")
+                   help="core-set picks per round (1 = GEMV form, 8 = one pass per round, 16 = two passes per round); default 16")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-prune", action="store_true", help="core-set passes stream every tile (exact pruning off)")
     p.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather per round instead of the peer-memory mailbox")
@@ -179,7 +178,7 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if a.batch is None:
-        a.batch = 16 if world >= 4 else 8
+        a.batch = 16    # two 8-centre passes per round: measured best at every GPU count once the passes are pruned
     local = int(os.environ.get("LOCAL_RANK", 0))
     n = a.frames
     n_lab = int(n * a.labeled_frac)

@@ -75,5 +75,5 @@ def test_pruned_selection_matches_oracle(built_lib):
     for batch in (8, 16):
         p, md, s = _select(v, torch.from_numpy(X).cuda(), torch.from_numpy(unc).cuda(), [], 120, 0.6, batch, "on")
         assert p.cpu().tolist() == ref, batch
-        assert np.allclose(md.cpu().numpy(), md_ref, rtol=1e-9, atol=1e-9)
+        assert np.allclose(md.cpu().numpy(), md_ref, rtol=1e-9, atol=1e-6)   # sklearn's d(c,c) is ~1e-7, ours exactly 0
         assert s["streamed"] < s["tiles"]

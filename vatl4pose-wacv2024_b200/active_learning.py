@@ -189,7 +189,7 @@ def coreset_selection(self, embeddings, uncertainty):
         rule = "w_unc"
     picks, stats, _, unc_after = ops.coreset_select(
         X, unc, labeled, int(self.query_size), float(self.moks_queried), float(self.unc_lambda), rule=rule,
-        first_pick=first_pick, batch=int(getattr(self, "coreset_batch", 8)), return_state=True)
+        first_pick=first_pick, batch=int(getattr(self, "coreset_batch", 16)), return_state=True)
     self.coreset_stats = stats
     if isinstance(uncertainty, np.ndarray):
         uncertainty[:] = unc_after.cpu().numpy()
@@ -250,7 +250,7 @@ class ActiveLearning:
         self.is_early_stop = False
         self.eval_joints = list(range(ops.J))
         self.hm_size = cfg.DATA_PRESET.HEATMAP_SIZE
-        self.coreset_batch = int(getattr(opt, "coreset_batch", 8))
+        self.coreset_batch = int(getattr(opt, "coreset_batch", 16))
         self.last_query = None
 
     # -- dispatch guard: names this package does not accelerate stay on the reference ----

@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
 // the pruned pass writes exactly the bits the full pass would: the pick list cannot change.  A
 // picked row is never pruned (its own segment has d(a_s,c) <= R_s).  VATLQ_PRUNE=verify streams
 // everything and counts rows of flagged tiles whose min_d moved (tests assert 0).
-constexpr int kSegMax = 64;
+constexpr int kSegMax = 64;   // <= 64: the filter reads a segment's min_d as two values per lane
 struct PruneCtl {
   double sum;                      // sum of the finite consecutive-row distances
   unsigned long long cnt;
@@ -1019,61 +1019,102 @@ __global__ void __launch_bounds__(256) seg_radius_kernel(const float* __restrict
   }
 }
 
-// per pass: seg_skip[s] = 1 when no row of segment s can get closer to this pass's centres
-__global__ void __launch_bounds__(256) prune_filter_kernel(const float* __restrict__ X, int d4, long long lo,
-                                                           const int* __restrict__ seg_start, const double* __restrict__ segR,
-                                                           const double* __restrict__ m, const double* __restrict__ xx,
-                                                           const Ctl* ctl, int center_off, const PruneCtl* pc,
-                                                           unsigned char* __restrict__ seg_skip) {
-  const int total = ctl->nb;
-  const int nb = min(kB, total - center_off);
+// per pass: seg_skip[s] = 1 when no row of segment s can get closer to this pass's centres.
+// Same tile machine as the candidate-pairs kernel (d == 8 * 16 * STEPS): the 8 warps of a CTA are
+// the 8 K-segments, each holding its 1/8 of the pass's 8 centres in registers as fp64 B operands;
+// tiles of 8 anchor rows stream through a register ring (the next tile's loads are in flight while
+// this one is multiplied, so the kernel is not a chain of memory round trips); after the split-K
+// exchange warp w finishes segment w of the tile: canonical distances of its anchor to the 8
+// centres, the maximum of min_d over its rows, and the test.
+template <int STEPS>
+__global__ void __launch_bounds__(kSeg * 32, 1) prune_filter_kernel(const float* __restrict__ X, int d4, long long lo,
+                                                                    const int* __restrict__ seg_start,
+                                                                    const double* __restrict__ segR,
+                                                                    const double* __restrict__ m, const double* __restrict__ xx,
+                                                                    const Ctl* ctl, int center_off, const PruneCtl* pc,
+                                                                    unsigned char* __restrict__ seg_skip) {
+  __shared__ __align__(16) double s_part[2][kSeg][64];
+  __shared__ double s_xxc[kB];
+  const int nb = min(kB, ctl->nb - center_off);
   if (nb <= 0) return;
-  __shared__ long long s_c[kB];
-  __shared__ double s_cn;
-  if (threadIdx.x < kB) s_c[threadIdx.x] = ctl->picks[center_off + min((int)threadIdx.x, nb - 1)];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double mx = 0.0;
-    for (int j = 0; j < kB; ++j) mx = fmax(mx, xx[s_c[j]]);
-    s_cn = sqrt(mx);
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const float4* X4 = reinterpret_cast<const float4*>(X);
   const int nseg = pc->nseg;
-  for (int sg = w0; sg < nseg; sg += nwarps) {
-    const int a = seg_start[sg], e = seg_start[sg + 1];
-    double M = 0.0;
-    for (int r = a + lane; r < e; r += 32) M = fmax(M, m[lo + r]);
+  const int ntiles = (nseg + 7) / 8;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  const int lane_off = seg * (STEPS * 4) + kk;
+  auto anchor = [&](int sg) -> long long { return lo + seg_start[min(sg, nseg - 1)]; };
+  int t = blockIdx.x;
+  // the first tile's anchor rows and the centres are requested back to back (one memory round trip)
+  float4 ring[STEPS];
+  {
+    const float4* p0 = X4 + (size_t)anchor(t * 8 + g) * d4 + lane_off;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
-    unsigned char skip = 0;
-    if (isfinite(M)) {
-      const float4* ap = X4 + (size_t)(lo + a) * d4;
-      double acc[kB];
+    for (int s = 0; s < STEPS; ++s) ring[s] = __ldg(p0 + 4 * s);
+  }
+  double breg[STEPS][4];
+  {
+    const long long p = ctl->picks[center_off + min(g, nb - 1)];   // padded with the last centre
+    const float4* cp = X4 + (size_t)p * d4 + lane_off;
 #pragma unroll
-      for (int j = 0; j < kB; ++j) acc[j] = 0.0;
-      for (int c = lane; c < d4; c += 32) {
-        const float4 u = __ldg(ap + c);
-#pragma unroll
-        for (int j = 0; j < kB; ++j) {
-          const float4 v = __ldg(X4 + (size_t)s_c[j] * d4 + c);
-          const double a0 = (double)u.x - (double)v.x, a1 = (double)u.y - (double)v.y;
-          const double a2 = (double)u.z - (double)v.z, a3 = (double)u.w - (double)v.w;
-          acc[j] = fma(a0, a0, acc[j]);
-          acc[j] = fma(a1, a1, acc[j]);
-          acc[j] = fma(a2, a2, acc[j]);
-          acc[j] = fma(a3, a3, acc[j]);
-        }
-      }
-      double d2min = INFINITY;
-#pragma unroll
-      for (int j = 0; j < kB; ++j) d2min = fmin(d2min, warp_sum(acc[j]));
-      const double margin = 1e-6 * (1.0 + sqrt(xx[lo + a]) + s_cn);
-      skip = (sqrt(d2min) - segR[sg] - M >= margin) ? 1 : 0;
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 c4 = __ldg(cp + 4 * s);
+      breg[s][0] = (double)c4.x;
+      breg[s][1] = (double)c4.y;
+      breg[s][2] = (double)c4.z;
+      breg[s][3] = (double)c4.w;
     }
-    if (lane == 0) seg_skip[sg] = skip;
+  }
+  if (threadIdx.x < kB) s_xxc[threadIdx.x] = xx[ctl->picks[center_off + min((int)threadIdx.x, nb - 1)]];
+  int buf = 0;
+  for (; t < ntiles; t += gridDim.x) {
+    const int tn = t + gridDim.x;
+    const bool has_next = tn < ntiles;
+    const float4* np = X4 + (size_t)anchor((has_next ? tn : t) * 8 + g) * d4 + lane_off;
+    const int myseg = t * 8 + seg;                       // the segment this warp finishes
+    // everything the test needs is requested BEFORE the multiply loop and consumed after it:
+    // min_d of the segment's rows (segments hold <= kSegMax = 64 rows: two per lane), |a|^2, R
+    double m0 = 0.0, m1 = 0.0, xxa = 0.0, R = 0.0;
+    if (myseg < nseg) {
+      const int a = seg_start[myseg], e = seg_start[myseg + 1];
+      if (a + lane < e) m0 = m[lo + a + lane];
+      if (a + lane + 32 < e) m1 = m[lo + a + lane + 32];
+      xxa = xx[lo + a];
+      R = segR[myseg];
+    }
+    double c[4][2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4 x = ring[s];
+      if (has_next) ring[s] = __ldg(np + 4 * s);
+      dmma(c[0], (double)x.x, breg[s][0]);
+      dmma(c[1], (double)x.y, breg[s][1]);
+      dmma(c[2], (double)x.z, breg[s][2]);
+      dmma(c[3], (double)x.w, breg[s][3]);
+    }
+    *reinterpret_cast<double2*>(&s_part[buf][seg][lane * 2]) =
+        make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
+    __syncthreads();
+    if (myseg < nseg) {
+      double M = fmax(m0, m1);
+      double d2 = INFINITY;
+      if (lane < kB) d2 = sq_from_dot(combine8(&s_part[buf][0][seg * 8 + lane], 64), xxa, s_xxc[lane]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+        d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+      }
+      if (lane == 0) {
+        double cn = 0.0;
+#pragma unroll
+        for (int j = 0; j < kB; ++j) cn = fmax(cn, s_xxc[j]);
+        const double margin = 1e-6 * (1.0 + sqrt(xxa) + sqrt(cn));
+        seg_skip[myseg] = (isfinite(M) && sqrt(fmax(d2, 0.0)) - R - M >= margin) ? 1 : 0;
+      }
+    }
+    buf ^= 1;
   }
 }
 
@@ -1923,6 +1964,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     pairs_cfg = true;
   }
+  // tiles of 8 segments, grid-stride: one CTA per SM at most
+  const int filter_grid = std::max(1, std::min(sm_count(), own / 8 + 1));
   auto fill_pass = [&](PassArgs& a) {
     a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.n_centers_imm = 0; a.ctl = ctl;
@@ -2008,8 +2051,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         a.center_off = off;
         a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
         if (prune_mode) {
-          prune_filter_kernel<<<sm_count() * 4, 256, 0, stream>>>(X, G.d4, row_lo, seg_start, seg_r, min_d, xx, ctl, off, pc,
-                                                                 seg_skip);
+          prune_filter_kernel<16><<<filter_grid, kSeg * 32, 0, stream>>>(X, G.d4, row_lo, seg_start, seg_r, min_d, xx, ctl, off,
+                                                                        pc, seg_skip);
           g_launches.fetch_add(1);
         }
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;

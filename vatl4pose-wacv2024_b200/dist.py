@@ -126,7 +126,7 @@ class Comm:
 
 def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_local, ae_weights, labeled_global,
                       n: int, k: int, moks: float = 0.0, lam: float = 0.01, uncertainty: str = "THC+WPU",
-                      thc_vs_wpu: str = "const", rule: str = "w_unc", batch: int = 8, comm: Comm | None = None,
+                      thc_vs_wpu: str = "const", rule: str = "w_unc", batch: int = 16, comm: Comm | None = None,
                       group=None, first_pick: int = -1):
     """One query over a pool sharded across the ranks of `group` (one process per GPU).
     Every rank passes its slice of the pool and gets the same global pick list back."""

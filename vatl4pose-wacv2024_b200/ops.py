@@ -208,7 +208,7 @@ class CoresetStats:
 
 
 def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: float, lam: float,
-                   rule: str = "w_unc", first_pick: int = -1, batch: int = 8, comm=None,
+                   rule: str = "w_unc", first_pick: int = -1, batch: int = 16, comm=None,
                    row_range: tuple[int, int] | None = None, return_state: bool = False):
     """k-center greedy selection (vatlq_coreset_init + vatlq_coreset_select).
     X (n,d) fp32 CUDA (replicated on every rank when comm is given), unc (n,) fp64 CUDA — a

@@ -190,7 +190,7 @@ class QueryPass:
 
 def run_query(H, boxes_xyxy, is_prev, is_next, X, ae_weights, labeled, k: int, moks: float = 0.0,
               lam: float = 0.01, uncertainty: str = "THC+WPU", thc_vs_wpu: str = "const", rule: str = "w_unc",
-              batch: int = 8, device="cuda:0", chunk: int | None = None, first_pick: int = -1) -> QueryResult:
+              batch: int = 16, device="cuda:0", chunk: int | None = None, first_pick: int = -1) -> QueryResult:
     """One full single-GPU query (THC + WPU + fusion + core-set) — the public functional API.
     Inputs may be host numpy arrays / CPU tensors (copied to `device` here, chunk by chunk for
     the heat maps) or CUDA tensors (used in place)."""

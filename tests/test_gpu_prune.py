@@ -77,3 +77,21 @@ def test_pruned_selection_matches_oracle(built_lib):
         assert p.cpu().tolist() == ref, batch
         assert np.allclose(md.cpu().numpy(), md_ref, rtol=1e-9, atol=1e-6)   # sklearn's d(c,c) is ~1e-7, ours exactly 0
         assert s["streamed"] < s["tiles"]
+
+
+def test_labelled_set_initialisation_is_pruned_exactly(built_lib):
+    """The labelled-set initialisation (vatlq_coreset_init: n_labeled/8 passes) is pruned with the same
+    filter: identical min_d / picks with a 20 % labelled set, fewer tiles streamed."""
+    v = built_lib
+    n = 30000
+    X = v.synth.device_embeddings(n, "cuda:0", seed=17)
+    rng = np.random.default_rng(18)
+    lab = sorted(rng.choice(n, n // 5, replace=False).tolist())
+    u = rng.uniform(0, 1, n); u[lab] = 0
+    unc = torch.from_numpy(u).cuda()
+    p_off, md_off, s_off = _select(v, X, unc, lab, 24, 0.6, 8, "off")
+    p_on, md_on, s_on = _select(v, X, unc, lab, 24, 0.6, 8, "on")
+    _, md_ver, s_ver = _select(v, X, unc, lab, 24, 0.6, 8, "verify")
+    assert torch.equal(p_off, p_on) and torch.equal(md_off, md_on) and torch.equal(md_off, md_ver)
+    assert s_ver["violations"] == 0
+    assert s_ver["tiles"] > 700 * (n // 8)                 # the 750 initialisation passes were counted (verify collects them)

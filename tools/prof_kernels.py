@@ -1,5 +1,9 @@
-"""Short driver for ncu captures: one heat-map scan and a few core-set passes at bench scale.
-    ncu --set full --clock-control none --import-source on -k regex:'scan_tma|pass_kernel' -o gpurun_out/prof python tools/prof_kernels.py
+"""Short driver for ncu captures at bench scale: one heat-map scan, the 8f kernels, and a core-set
+selection long enough to reach the pruned steady state.
+    ncu --set full --clock-control none --import-source on -k regex:'pass_kernel_tma|prune_filter|pairs_plan' \
+        --launch-skip 1500 -c 8 -o gpurun_out/prof_coreset python tools/prof_kernels.py
+    ncu --set full --clock-control none -k regex:'scan_tma|entropy_kernel|cos_colsum_kernel|cos_rowsum' -c 6 \
+        -o gpurun_out/prof_stream python tools/prof_kernels.py
 """
 import os
 import sys
@@ -11,16 +15,18 @@ from vatlq import ops, synth
 
 frames = int(os.environ.get("PROF_FRAMES", 20000))
 rows = int(os.environ.get("PROF_ROWS", 170000))
-k = int(os.environ.get("PROF_K", 40))
-batch = int(os.environ.get("PROF_BATCH", 8))
+k = int(os.environ.get("PROF_K", 5200))
+batch = int(os.environ.get("PROF_BATCH", 16))
 dev = "cuda:0"
 H, ip, inx, bb = synth.device_pool(frames, dev, seed=1)
 for _ in range(2):
     r = ops.heatmap_scan(H, ip, inx, bb)
+ops.heatmap_entropy(H)
 torch.cuda.synchronize()
 del H
 X = synth.device_embeddings(rows, dev, seed=2)
+ops.cosine_rowsum(X)
 unc = torch.rand(rows, dtype=torch.float64, device=dev)
-picks, st = ops.coreset_select(X, unc, [], k, 0.6, 0.01, batch=batch)
+picks, st = ops.coreset_select(X, unc, [], k, 0.0, 0.01, batch=batch)
 torch.cuda.synchronize()
-print("ok", st)
+print("ok", st, ops.prune_stats())

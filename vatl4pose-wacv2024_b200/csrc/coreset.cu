@@ -1031,12 +1031,14 @@ __global__ void __launch_bounds__(kSeg * 32, 1) prune_filter_kernel(const float*
                                                                     const int* __restrict__ seg_start,
                                                                     const double* __restrict__ segR,
                                                                     const double* __restrict__ m, const double* __restrict__ xx,
-                                                                    const Ctl* ctl, int center_off, const PruneCtl* pc,
-                                                                    unsigned char* __restrict__ seg_skip) {
+                                                                    const long long* __restrict__ centers_all,
+                                                                    const int* n_centers, int n_centers_imm, int center_off,
+                                                                    const PruneCtl* pc, unsigned char* __restrict__ seg_skip) {
   __shared__ __align__(16) double s_part[2][kSeg][64];
   __shared__ double s_xxc[kB];
-  const int nb = min(kB, ctl->nb - center_off);
+  const int nb = min(kB, (n_centers ? *n_centers : n_centers_imm) - center_off);   // like pass_centers()
   if (nb <= 0) return;
+  const long long* centers = centers_all + center_off;
   const int nseg = pc->nseg;
   const int ntiles = (nseg + 7) / 8;
   if ((int)blockIdx.x >= ntiles) return;
@@ -1054,7 +1056,7 @@ __global__ void __launch_bounds__(kSeg * 32, 1) prune_filter_kernel(const float*
   }
   double breg[STEPS][4];
   {
-    const long long p = ctl->picks[center_off + min(g, nb - 1)];   // padded with the last centre
+    const long long p = centers[min(g, nb - 1)];   // padded with the last centre
     const float4* cp = X4 + (size_t)p * d4 + lane_off;
 #pragma unroll
     for (int s = 0; s < STEPS; ++s) {
@@ -1065,7 +1067,7 @@ __global__ void __launch_bounds__(kSeg * 32, 1) prune_filter_kernel(const float*
       breg[s][3] = (double)c4.w;
     }
   }
-  if (threadIdx.x < kB) s_xxc[threadIdx.x] = xx[ctl->picks[center_off + min((int)threadIdx.x, nb - 1)]];
+  if (threadIdx.x < kB) s_xxc[threadIdx.x] = xx[centers[min((int)threadIdx.x, nb - 1)]];
   int buf = 0;
   for (; t < ntiles; t += gridDim.x) {
     const int tn = t + gridDim.x;
@@ -1831,6 +1833,68 @@ static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullp
   return 0;
 }
 
+// ---- exact pruning: mode resolution and per-call set-up shared by init and select
+struct PruneState {
+  int mode = 0;   // 0 off, 1 prune, 2 verify
+  PruneCtl* pc = nullptr;
+  int* seg_of_row = nullptr;
+  int* seg_start = nullptr;
+  double* seg_r = nullptr;
+  unsigned char* seg_skip = nullptr;
+  int filter_grid = 1;
+};
+static int prune_setup(PruneState& P, const float* X, const Geom& G, int64_t row_lo, int64_t row_hi, char* w,
+                       const WsLayout& L, cudaStream_t stream) {
+  static const int prune_env = []() {
+    const char* e = getenv("VATLQ_PRUNE");
+    if (!e) return 1;
+    if (!strcmp(e, "0") || !strcmp(e, "off")) return 0;
+    return !strcmp(e, "verify") ? 2 : 1;
+  }();
+  static const long long prune_min_rows = []() {
+    const char* e = getenv("VATLQ_PRUNE_MIN_ROWS");
+    return e ? atoll(e) : 8192LL;
+  }();
+  const long long own = row_hi - row_lo;
+  P.pc = (PruneCtl*)(w + L.prune);
+  P.seg_of_row = (int*)(w + L.seg_of_row);
+  P.seg_start = (int*)(w + L.seg_start);
+  P.seg_r = (double*)(w + L.seg_r);
+  P.seg_skip = (unsigned char*)(w + L.seg_skip);
+  const long long prune_min = g_prune_min_set >= 0 ? g_prune_min_set : prune_min_rows;
+  P.mode = (G.d4 == kSeg * 4 * 16 && own >= prune_min && own >= 8 && own < (1LL << 30))
+               ? (g_prune_mode_set >= 0 ? g_prune_mode_set : prune_env) : 0;
+  P.filter_grid = (int)std::max<long long>(1, std::min<long long>(sm_count(), own / 8 + 1));   // tiles of 8 segments, grid-stride
+  VQ_CUDA(cudaMemsetAsync(P.pc, 0, sizeof(PruneCtl), stream));
+  if (P.mode) {
+    double* cd = (double*)(w + L.dots);   // the dot-product scratch is idle until the first pass
+    consec_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, row_hi, cd, P.pc);
+    VQ_LAUNCHED();
+    segment_kernel<<<1, 1024, 0, stream>>>(cd, (int)own, P.pc, P.seg_of_row, P.seg_start);
+    VQ_LAUNCHED();
+    seg_radius_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, P.seg_start, P.pc, P.seg_r);
+    VQ_LAUNCHED();
+  }
+  return 0;
+}
+// flags for the pass that applies centers[center_off ..): launched right before that pass
+static int launch_filter(const PruneState& P, const PassArgs& a, cudaStream_t stream) {
+  prune_filter_kernel<16><<<P.filter_grid, kSeg * 32, 0, stream>>>(a.X, a.d4, a.lo, P.seg_start, P.seg_r, a.m, a.xx, a.centers,
+                                                                  a.n_centers, a.n_centers_imm, a.center_off, P.pc, P.seg_skip);
+  VQ_LAUNCHED();
+  return 0;
+}
+// accumulate the device-side tile statistics of a finished call (the caller has synchronised)
+static void prune_collect(const PruneState& P) {
+  PruneCtl hp{};
+  if (cudaMemcpy(&hp, P.pc, sizeof(PruneCtl), cudaMemcpyDeviceToHost) == cudaSuccess) {
+    g_prune[0] += (long long)hp.stats[0];
+    g_prune[1] += (long long)hp.stats[1];
+    g_prune[2] += (long long)hp.stats[2];
+    g_prune[3] = hp.nseg;
+  }
+}
+
 extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
                                   const int64_t* labeled, int64_t n_labeled, double* min_d, void* ws,
                                   size_t ws_bytes, vatlq_stream_t stream_) {
@@ -1846,13 +1910,25 @@ extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_
   VQ_REQUIRE(labeled != nullptr, "labeled is null");
   if (int e = launch_norms(X, n, d, xx, stream)) return e;
   const Geom G = geom_of(d);
+  // the labelled set is applied 8 centres per pass; as soon as a track holds a labelled row the
+  // later passes stop streaming it (same exact pruning as the selection passes)
+  PruneState P;
+  if (int e = prune_setup(P, X, G, row_lo, row_hi, w, L, stream)) return e;
   for (int64_t c0 = 0; c0 < n_labeled; c0 += kB) {
     PassArgs a{};
     a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.dots = (double*)(w + L.dots);
     a.unc = nullptr; a.score = nullptr; a.centers = (const long long*)labeled + c0; a.n_centers = nullptr;
     a.n_centers_imm = (int)std::min<int64_t>(kB, n_labeled - c0); a.ctl = nullptr; a.hist = nullptr;
+    if (P.mode) {
+      a.seg_of_row = P.seg_of_row; a.seg_skip = P.seg_skip; a.prune_mode = P.mode; a.prune_stats = P.pc->stats;
+      if (int e = launch_filter(P, a, stream)) return e;
+    }
     if (int e = launch_pass(a, stream)) return e;
+  }
+  if (P.mode == 2) {   // verify mode only: wait and collect the violation count of the initialisation passes
+    VQ_CUDA(cudaStreamSynchronize(stream));
+    prune_collect(P);
   }
   return 0;
 }
@@ -1927,34 +2003,9 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
 
   const int own = (int)std::min<int64_t>(row_hi - row_lo, 1LL << 30);
   // ---- exact pruning set-up (fast path only): segments of near-consecutive rows, anchors, radii
-  static const int prune_env = []() {
-    const char* e = getenv("VATLQ_PRUNE");
-    if (!e) return 1;
-    if (!strcmp(e, "0") || !strcmp(e, "off")) return 0;
-    return !strcmp(e, "verify") ? 2 : 1;
-  }();
-  static const long long prune_min_rows = []() {
-    const char* e = getenv("VATLQ_PRUNE_MIN_ROWS");
-    return e ? atoll(e) : 8192LL;
-  }();
-  PruneCtl* pc = (PruneCtl*)(w + L.prune);
-  int* seg_of_row = (int*)(w + L.seg_of_row);
-  int* seg_start = (int*)(w + L.seg_start);
-  double* seg_r = (double*)(w + L.seg_r);
-  unsigned char* seg_skip = (unsigned char*)(w + L.seg_skip);
-  const long long prune_min = g_prune_min_set >= 0 ? g_prune_min_set : prune_min_rows;
-  const int prune_mode = (G.d4 == kSeg * 4 * 16 && row_hi - row_lo >= prune_min && row_hi - row_lo >= 8 && row_hi - row_lo < (1LL << 30))
-                             ? (g_prune_mode_set >= 0 ? g_prune_mode_set : prune_env) : 0;
-  VQ_CUDA(cudaMemsetAsync(pc, 0, sizeof(PruneCtl), stream));
-  if (prune_mode) {
-    double* cd = (double*)(w + L.dots);   // the dot-product scratch is idle until the first pass
-    consec_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, row_hi, cd, pc);
-    VQ_LAUNCHED();
-    segment_kernel<<<1, 1024, 0, stream>>>(cd, own, pc, seg_of_row, seg_start);
-    VQ_LAUNCHED();
-    seg_radius_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, G.d4, row_lo, seg_start, pc, seg_r);
-    VQ_LAUNCHED();
-  }
+  PruneState P;
+  if (int e = prune_setup(P, X, G, row_lo, row_hi, w, L, stream)) return e;
+  const int prune_mode = P.mode;
   int fgrid = std::max(1, std::min(sm_count() * 4, (own + 255) / 256));
   VQ_REQUIRE(fgrid <= 4096 && sm_count() <= 4096, "grid too large for the arg-max scratch");
   const size_t pairs_smem = G.smem;
@@ -1964,15 +2015,13 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     pairs_cfg = true;
   }
-  // tiles of 8 segments, grid-stride: one CTA per SM at most
-  const int filter_grid = std::max(1, std::min(sm_count(), own / 8 + 1));
   auto fill_pass = [&](PassArgs& a) {
     a.X = X; a.n = n; a.d4 = G.d4; a.nss = G.nss; a.S = G.S; a.lo = row_lo; a.hi = row_hi; a.xx = xx; a.m = min_d;
     a.unc = unc; a.score = score; a.centers = ctl->picks; a.n_centers = &ctl->nb; a.n_centers_imm = 0; a.ctl = ctl;
     a.hist = (nbk > 1) ? hist : nullptr; a.send = send; a.partial = partial; a.dots = (double*)(w + L.dots);
-    a.prune_stats = pc->stats;
+    a.prune_stats = P.pc->stats;
     if (prune_mode) {
-      a.seg_of_row = seg_of_row; a.seg_skip = seg_skip; a.prune_mode = prune_mode;
+      a.seg_of_row = P.seg_of_row; a.seg_skip = P.seg_skip; a.prune_mode = prune_mode;
     }
   };
 
@@ -2050,11 +2099,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         fill_pass(a);
         a.center_off = off;
         a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
-        if (prune_mode) {
-          prune_filter_kernel<16><<<filter_grid, kSeg * 32, 0, stream>>>(X, G.d4, row_lo, seg_start, seg_r, min_d, xx, ctl, off,
-                                                                        pc, seg_skip);
-          g_launches.fetch_add(1);
-        }
+        if (prune_mode) rc = launch_filter(P, a, stream);
+        if (rc) break;
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
         rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
@@ -2104,15 +2150,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       rc = VATLQ_ECOMM;
     }
   }
-  if (rc == 0) {
-    PruneCtl hp{};
-    if (cudaMemcpy(&hp, pc, sizeof(PruneCtl), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      g_prune[0] += (long long)hp.stats[0];
-      g_prune[1] += (long long)hp.stats[1];
-      g_prune[2] += (long long)hp.stats[2];
-      g_prune[3] = hp.nseg;
-    }
-  }
+  if (rc == 0) prune_collect(P);
   if (rc == 0 && host_stats) {
     const Ctl* hc = (const Ctl*)h_picked;
     host_stats[0] = hc->stat_passes;

@@ -312,6 +312,37 @@ def main():
                 "share_of_step": tot_ms.value / a.steps / ms_step,
                 "note": "frac charges a pass the bytes it moves ONCE although it applies greedy_steps_per_launch "
                         "greedy steps (exact batching); greedy_equivalent_gbs is SURVEY 8d's per-step bytes x steps / time"}
+    # ---- the same kernel with pruning off (one extra, untimed-for-`value` query): how fast the pass streams
+    # when it has to read every row — the pruned launches are short, so launch/prologue/epilogue weigh more
+    if roof is not None and not a.no_prune and world == 1:
+        unpruned = None
+        try:
+            ops.set_prune("off")
+            lib.vatlq_profile_passes(1)
+            lib.vatlq_profile_read(None, None, None, 1)
+            step_resident()
+            torch.cuda.synchronize()
+            t2, n2, p2 = C.c_double(), C.c_int64(), C.c_int64()
+            lib.vatlq_profile_read(C.byref(t2), C.byref(n2), C.byref(p2), 1)
+            if n2.value > 0 and t2.value > 0:
+                full = nl * D * 4 + 40 * nl
+                s2 = t2.value / n2.value * 1e-3
+                unpruned = {"achieved": full / s2 / 1e9, "frac": full / s2 / 1e9 / peak_gbs, "avg_launch_us": s2 * 1e6,
+                            "launches_timed": n2.value, "algorithmic_bytes_per_launch": full,
+                            "traffic": ncu_traffic("pass_kernel", nl)}
+        except Exception as exc:  # report, never hide; the headline numbers above are unaffected
+            unpruned = {"error": repr(exc)[:200]}
+        finally:
+            try:
+                lib.vatlq_profile_passes(0)
+                ops.set_prune("env")
+                ops.prune_stats(reset=True)
+            except Exception:
+                pass
+        roof["unpruned_pass"] = unpruned
+        roof["note"] += ("; with exact pruning a launch streams only streamed_fraction_of_X of the rows, so its fixed "
+                         "costs weigh more: unpruned_pass is the same kernel timed in one extra query with pruning off")
+
     # ---- the streaming kernel: heat-map scan, timed alone on this rank's shard
     scan_roof = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -32,6 +32,11 @@ class QueryResult:
     extra: dict = field(default_factory=dict)
 
 
+def _require_cuda(dev: torch.device):
+    if dev.type != "cuda":
+        raise _lib.VatlqError("QueryPass needs a CUDA device")
+
+
 SINGLE_UNCERTAINTIES = ("HP", "TPC", "Entropy")   # one fp32 score per item, min-max normalised (:511-516)
 
 
@@ -41,8 +46,7 @@ class QueryPass:
     def __init__(self, n_local: int, device, ae_weights=None, uncertainty: str = "THC+WPU",
                  n_joints: int = ops.J, hm_shape=(ops.HM_H, ops.HM_W), keep_kpts: bool = True):
         self.dev = torch.device(device)
-        if self.dev.type != "cuda":
-            raise _lib.VatlqError("QueryPass needs a CUDA device")
+        _require_cuda(self.dev)
         _lib.lib()  # fail now, loudly, if the CUDA library is missing
         self.n = int(n_local)
         self.uncertainty = uncertainty

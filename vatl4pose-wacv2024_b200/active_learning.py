@@ -322,11 +322,11 @@ class ActiveLearning:
         wpu_h = qp.wpu.cpu().numpy() if qp.use_wpu else None
         if self.uncertainty == "THC+WPU":
             total_unc = float(thc_h.astype(np.float64).sum())
-            UNC = {i: [float(thc_h[i]), float(wpu_h[i])] for i in range(n)}
+            UNC = {i: [t, w] for i, (t, w) in enumerate(zip(thc_h.tolist(), wpu_h.tolist()))}
         elif qp.use_thc or qp.use_wpu or qp.single:
             v = qp.single_score().cpu().numpy() if qp.single else (thc_h if qp.use_thc else wpu_h)
             total_unc = float(v.astype(np.float64).sum())
-            UNC = {i: float(v[i]) for i in range(n)}
+            UNC = dict(enumerate(v.tolist()))
         else:
             total_unc, UNC = 0.0, {i: 0 for i in range(n)}
         self.uncertainty_mean.append(total_unc / n)                                   # (:466)

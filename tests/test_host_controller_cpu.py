@@ -120,11 +120,13 @@ def _install_stand_ins(monkeypatch, v):
         p = torch.tensor(picks, dtype=torch.int64)
         return (p, None, None, torch.from_numpy(u)) if return_state else (p, None)
 
-    def wpu(kpts, boxes, packed, in_dim, z_dim, drop_ears=False, return_features=False, check_status=True):
+    def wpu(kpts, boxes, packed, in_dim, z_dim, drop_ears=False, return_features=False, check_status=True,
+            return_status=False):
         ae = packed[0]   # pack_ae_weights stand-in below keeps the torch module
         out = [O.wpu_item(ae, [float(x) for x in boxes[i]], kpts[i].reshape(-1).double().numpy(), drop_ears)
                for i in range(kpts.shape[0])]
-        return torch.tensor(out, dtype=torch.float32)
+        w = torch.tensor(out, dtype=torch.float32)
+        return (w, torch.zeros(len(out), dtype=torch.uint8)) if return_status else w
 
     def pack_ae_weights(weights, device):
         return [O.make_autoencoder(weights)], 42, 4

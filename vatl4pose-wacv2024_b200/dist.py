@@ -32,13 +32,14 @@ def shard_sizes(n: int, world: int) -> list[int]:
 def exchange_halo(first: torch.Tensor | None, last: torch.Tensor | None, rank: int, world: int, group=None):
     """Send this rank's first frame to rank-1 and last frame to rank+1; return
     (halo_prev, halo_next): the frame before / after the local range (None at the pool ends).
-    Frames are one (J,h,w) tensor = 208 896 B at the reference shape; an empty shard passes
-    the frames it receives through unchanged so that chains of small shards stay correct."""
+    Frames are one (J,h,w) tensor = 208 896 B at the reference shape.  Every rank must own at
+    least one frame (shard_range guarantees it for n >= world); an empty shard raises."""
     if world == 1:
         return None, None
     like = first if first is not None else last
     if like is None:
-        raise _lib.VatlqError("exchange_halo: empty shards need a template frame")
+        raise _lib.VatlqError("exchange_halo: an empty shard is not supported (shard_range never produces one "
+                              "for n >= world); give every rank at least one frame")
     halo_prev = torch.empty_like(like) if rank > 0 else None
     halo_next = torch.empty_like(like) if rank < world - 1 else None
     ops_ = []
@@ -134,9 +135,15 @@ def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_loca
     from .query import QueryPass, QueryResult
     rank, world = td.get_rank(group), td.get_world_size(group)
     lo, hi = shard_range(n, rank, world)
-    dev = H_local.device
+    dev = X_local.device
     qp = QueryPass(hi - lo, dev, ae_weights=ae_weights, uncertainty=uncertainty)
-    hp, hn = exchange_halo(H_local[0] if hi > lo else None, H_local[-1] if hi > lo else None, rank, world, group)
+    if isinstance(H_local, (list, tuple)):     # (pos, tensor) segments in pool order
+        first = H_local[0][1][0] if H_local else None
+        last = H_local[-1][1][-1] if H_local else None
+    else:
+        first = H_local[0] if hi > lo else None
+        last = H_local[-1] if hi > lo else None
+    hp, hn = exchange_halo(first, last, rank, world, group)
     qp.score_pool(H_local, boxes_local, is_prev_local, is_next_local, halo_prev=hp, halo_next=hn)
     lab = np.asarray(list(labeled_global), dtype=np.int64)
     unl = torch.ones(hi - lo, dtype=torch.uint8, device=dev)

@@ -139,7 +139,8 @@ def pack_ae_weights(weights, device) -> tuple[torch.Tensor, int, int]:
 
 
 def wpu(kpts: torch.Tensor, boxes_xyxy: torch.Tensor, packed_weights: torch.Tensor, in_dim: int, z_dim: int,
-        drop_ears: bool = False, return_features: bool = False, check_status: bool = True):
+        drop_ears: bool = False, return_features: bool = False, check_status: bool = True,
+        return_status: bool = False):
     """Whole-body pose unnaturalness of every pose (vatlq_wpu).  kpts (n,17,3) fp32 CUDA."""
     kpts = _cuda(kpts, torch.float32, "kpts")
     n = kpts.shape[0]
@@ -159,6 +160,8 @@ def wpu(kpts: torch.Tensor, boxes_xyxy: torch.Tensor, packed_weights: torch.Tens
         if bad:  # the reference's AssertionErrors (hybrid_feature.py:25,31)
             raise AssertionError("height of human body must be positive!" if bad == 1
                                  else "at least one visible keypoint is required!")
+    if return_status:
+        return (out, feat, status) if return_features else (out, status)
     return (out, feat) if return_features else out
 
 

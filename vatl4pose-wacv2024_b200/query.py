@@ -75,6 +75,7 @@ class QueryPass:
         self._carry = None        # last frame of the previous chunk (halo_prev of the next)
         self._carry_pos = 0
         self._pending = None      # a chunk whose last frame still waits for its successor
+        self._wpu_status = None   # device scalar: worst per-pose status seen so far (checked in fuse())
         self.ae = None
         if self.use_wpu:
             if ae_weights is None:
@@ -120,8 +121,9 @@ class QueryPass:
                 self.thc[pos - 1] = fix.thc[0]
             if not last_chunk:
                 prev_of_last = H[m - 2] if m >= 2 else hp
-                ip = torch.as_tensor(np.asarray(is_prev.cpu() if isinstance(is_prev, torch.Tensor) else is_prev))[-1:]
-                inx = torch.as_tensor(np.asarray(is_next.cpu() if isinstance(is_next, torch.Tensor) else is_next))[-1:]
+                # (device slices of the flags: no host round trip per chunk)
+                ip = ops._flags(is_prev, m, self.dev, "is_prev")[m - 1:m].clone()
+                inx = ops._flags(is_next, m, self.dev, "is_next")[m - 1:m].clone()
                 self._pending = (H[m - 1:m].clone(), boxes_xyxy[m - 1:m].clone(), ip, inx,
                                  None if prev_of_last is None else prev_of_last.clone())
             else:
@@ -142,14 +144,26 @@ class QueryPass:
                 self._halo_xy[1] = ops.heatmap_scan(halo_next.reshape(1, *H.shape[1:])).coords_hm[0]
         if self.use_wpu:
             w, ind, z = self.ae
-            self.wpu[sl] = ops.wpu(res.kpts, boxes_xyxy, w, ind, z, drop_ears=not self.use_thc)
+            # invalid poses (hybrid_feature.py:25,31) are reported once, in fuse(): no host sync per chunk
+            self.wpu[sl], st = ops.wpu(res.kpts, boxes_xyxy, w, ind, z, drop_ears=not self.use_thc, check_status=False,
+                                       return_status=True)
+            self._wpu_status = st.max() if self._wpu_status is None else torch.maximum(self._wpu_status, st.max())
 
     def score_pool(self, H, boxes_xyxy, is_prev, is_next, halo_prev=None, halo_next=None, chunk: int | None = None):
-        """Score a pool that is already resident (one scan call, or chunked when asked)."""
+        """Score a pool that is already resident (one scan call, or chunked when asked).  `H` is the
+        (n,J,h,w) tensor, or a list of (pos, tensor) segments in pool order that together cover the
+        rank's items (a pool whose heat maps are held as several buffers, e.g. a resident ring)."""
         self._carry = None
         self._pending = None
+        self._wpu_status = None
         self._halo_xy = [None, None]
         self._aux_done = self.single not in ("HP", "TPC")
+        if isinstance(H, (list, tuple)):
+            for pos, seg in H:
+                e = pos + seg.shape[0]
+                self.score_chunk(pos, seg, boxes_xyxy[pos:e], is_prev[pos:e], is_next[pos:e],
+                                 halo_prev if pos == 0 else None, halo_next if e >= self.n else None)
+            return
         if chunk is None or chunk >= H.shape[0]:
             self.score_chunk(0, H, boxes_xyxy, is_prev, is_next, halo_prev, halo_next)
             return
@@ -176,6 +190,12 @@ class QueryPass:
              group=None, n_unlabeled_global: int | None = None) -> torch.Tensor:
         """ActiveLearning.py:486-530: combine weight + fused uncertainty (fp64, 0 on labelled rows)."""
         unl = unlabeled_mask.to(self.dev).to(torch.uint8)
+        if self._wpu_status is not None:
+            bad = int(self._wpu_status.item())
+            self._wpu_status = None
+            if bad:  # the reference's AssertionErrors (hybrid_feature.py:25,31)
+                raise AssertionError("height of human body must be positive!" if bad == 1
+                                     else "at least one visible keypoint is required!")
         n_unl = int(unl.sum().item()) if n_unlabeled_global is None else int(n_unlabeled_global)
         self.n_unlabeled = n_unl
         # combine_weight = sum over unlabelled of localpeak_mean / |U|   (:411-412,486-488)
@@ -204,12 +224,12 @@ def run_query(H, boxes_xyxy, is_prev, is_next, X, ae_weights, labeled, k: int, m
         t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
         return t.to(device=dev, dtype=dtype, non_blocking=True)
 
-    n = H.shape[0]
+    n = sum(t.shape[0] for _, t in H) if isinstance(H, (list, tuple)) else H.shape[0]
     qp = QueryPass(n, dev, ae_weights=ae_weights, uncertainty=uncertainty)
     bb = to_dev(boxes_xyxy, torch.float32)
     ip = to_dev(is_prev, torch.uint8)
     inx = to_dev(is_next, torch.uint8)
-    on_dev = isinstance(H, torch.Tensor) and H.is_cuda
+    on_dev = isinstance(H, (list, tuple)) or (isinstance(H, torch.Tensor) and H.is_cuda)
     if on_dev:
         qp.score_pool(H, bb, ip, inx, chunk=chunk)
     else:

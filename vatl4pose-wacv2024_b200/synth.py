@@ -178,7 +178,7 @@ def device_embeddings(n: int, device, d: int = FEAT_D, seed: int = 2):
 # item index, position), built from 32-bit integer hashes and single IEEE fp32 operations only,
 # so numpy on the host and torch on the GPU produce the SAME BITS for any slice of the pool.
 # That is what lets (a) every rank of an N-GPU run cut its shard out of ONE global pool,
-# (b) the CPU oracle run on exactly the pool the GPU benchmark uses (tests/golden/coreset_scale.npz),
+# (b) the CPU reference run (which pins the goldens) see exactly the pool the GPU benchmark uses (tests/golden/coreset_scale.npz),
 # (c) a pool larger than HBM be regenerated chunk by chunk.  Recipe and shapes follow SURVEY.md §8d
 # (sigma-2 blobs on drifting centres, N(0,0.02)-like noise, geometric tracks of mean length 30,
 # features = ceil(n/30) cluster centres ~ 0.5*ReLU(N(0,1)) + N(0,sigma) within-cluster noise);
@@ -387,3 +387,32 @@ def pool_boxes(n: int, lo: int = 0, hi: int | None = None, seed: int = 0, device
         return _f32(np.stack(cols, axis=1), 2)
     import torch
     return _f32(torch.stack(cols, dim=1), 2)
+
+
+def rank_pool(n: int, lo: int, hi: int, device, kind: str = "clustered", d: int = FEAT_D):
+    """Items [lo, hi) of the global counter-based pool, resident on `device`: returns
+    (heat-map segments [(pos, tensor)], boxes, is_prev, is_next, features, distinct frames held).
+    The heat-map content has period HEAT_RING items (a 1 M-frame pool is 208.9 GB of maps, more than one
+    GPU holds), so a range that spans whole periods keeps ONE copy of the ring and is scanned once per
+    period — the same HBM traffic as distinct frames."""
+    import torch
+    ring = HEAT_RING
+    tid, pos, ip, inx = pool_tracks(n, seed=0, ring=ring)
+    cuts = [lo]
+    while cuts[-1] < hi:
+        cuts.append(min(hi, (cuts[-1] // ring + 1) * ring))
+    segs = []
+    if hi - lo >= ring:
+        R = pool_heatmaps(tid, pos, 0, ring, seed=0, device=device, ring=ring)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            segs.append((a - lo, R[a % ring:a % ring + (b - a)]))
+        distinct = ring
+    else:
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            segs.append((a - lo, pool_heatmaps(tid, pos, a, b, seed=0, device=device, ring=ring)))
+        distinct = hi - lo
+    bb = pool_boxes(n, lo, hi, seed=0, device=device)
+    X = pool_embeddings(n, lo, hi, d=d, seed=2, kind=kind, device=device)
+    ipd = torch.from_numpy(ip[lo:hi].copy()).to(device)
+    inxd = torch.from_numpy(inx[lo:hi].copy()).to(device)
+    return segs, bb, ipd, inxd, X, distinct

@@ -136,8 +136,11 @@ int vatlq_fuse_final(const uint8_t* unlabeled, int64_t n, const double* stats2,
  *          set and applied 8 per pass over X.
  * out_idx[k] int64 picks in order (device).  min_d[n] fp64 in/out (initialised by
  * vatlq_coreset_init), unc[n] fp64 in/out (picked entries zeroed like :848).
- * host_stats (optional, 8 x int64, host memory, written at the end — the call then
- * synchronises): passes over X, picks, fallback picks, candidate overflow events, ...
+ * host_stats (optional, 16 x int64, host memory, written at the end — the call synchronises
+ * anyway): [0] passes over X, [1] picks, [2] rounds planned, [3] fallback rounds (nothing listed),
+ * [4] fallback rounds (list overflow), [5] sum of candidates, [6] rounds launched, [7] picks per
+ * round, [8..10] ns spent waiting for the peers' candidate blocks / in the candidate x candidate
+ * tiles / in the planner (summed over the rounds), [11..15] reserved.
  * ------------------------------------------------------------------------------------ */
 size_t vatlq_coreset_workspace_bytes(int64_t n, int d, int batch);
 int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
@@ -209,6 +212,13 @@ int vatlq_minmax_stats_f64(const double* v, const uint8_t* mask, int64_t n, doub
 /* out_i = cw*unc_i + (1-cw)*infl_i on rows with mask != 0, else 0 (ActiveLearning.py:519). */
 int vatlq_fuse_blend(const double* unc, const double* infl, const uint8_t* mask, int64_t n,
                      double combine_weight, double* out, vatlq_stream_t stream);
+
+/* OKS of every item against its ground-truth pose (active_learning/al_metric.py:42-69, call site
+ * ActiveLearning.py:309): kpts / gt_kpts [n,17,3] fp32 (x, y, score | visibility), bbox_ann_xyxy [n,4]
+ * (converted like alphapose/utils/bbox.py:91-97), oks[n] fp64.  The controller derives moks_queried
+ * (:858, the core-set's score weights :815-821) and the stopping criteria (:707-725) from it. */
+int vatlq_oks(const float* kpts, const float* gt_kpts, const float* bbox_ann_xyxy, int64_t n, double* oks,
+              vatlq_stream_t stream);
 
 /* Timing of the dominant kernel (the pass over X) for bench.py's roofline: when enabled,
  * vatlq_coreset_select brackets every pass launch with CUDA events on `stream`; read returns

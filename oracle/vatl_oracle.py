@@ -421,6 +421,43 @@ def diversity_select(X: np.ndarray, unlabeled_idx, total, k: int):
 
 
 # --------------------------------------------------------------------------------------
+# OKS (the evaluation the selection weights are derived from)
+# --------------------------------------------------------------------------------------
+OKS_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89]) / 10.0
+OKS_VARS = (OKS_SIGMAS * 2) ** 2
+
+
+def compute_oks(bb_xywh, predkpts, gtkpts) -> float:
+    """active_learning/al_metric.py:42-69 — OKS of a predicted pose (51 values) against the ground
+    truth, body area = GT box w*h; keypoints invisible in the GT are ignored, and when none is
+    visible the distance to the doubled box is used."""
+    d, g = np.array(predkpts), np.array(gtkpts)
+    xg, yg, vg = g[0::3], g[1::3], g[2::3]
+    k1 = np.count_nonzero(vg > 0)
+    x0, x1 = bb_xywh[0] - bb_xywh[2], bb_xywh[0] + bb_xywh[2] * 2
+    y0, y1 = bb_xywh[1] - bb_xywh[3], bb_xywh[1] + bb_xywh[3] * 2
+    area = bb_xywh[2] * bb_xywh[3]
+    xd, yd = d[0::3], d[1::3]
+    if k1 > 0:
+        dx, dy = xd - xg, yd - yg
+    else:
+        z = np.zeros(17)
+        dx = np.max((z, x0 - xd), axis=0) + np.max((z, xd - x1), axis=0)
+        dy = np.max((z, y0 - yd), axis=0) + np.max((z, yd - y1), axis=0)
+    e = (dx ** 2 + dy ** 2) / OKS_VARS / (area + np.spacing(1)) * 0.5
+    if k1 > 0:
+        e = e[vg > 0]
+    return np.sum(np.exp(-e)) / e.shape[0]
+
+
+def mean_oks_of_queries(query_list, oks_by_idx) -> float:
+    """active_learning/ActiveLearning.py:852-858 — mOKS of the newly queried items (in descending OKS
+    order, as get_retrain_id sorts them before np.mean)."""
+    vals = sorted((oks_by_idx[i] for i in query_list), reverse=True)
+    return np.mean(vals)
+
+
+# --------------------------------------------------------------------------------------
 # whole scoring loop (the CPU arm that bench.py times)
 # --------------------------------------------------------------------------------------
 

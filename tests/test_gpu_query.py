@@ -24,7 +24,7 @@ class FakeEstimator(torch.nn.Module):
         return self.X[crops[:, 0, 0, 0].long()]
 
 
-def loader(n, boxes, ip, inx, bs):
+def loader(n, boxes, ip, inx, bs, gt=None):
     for a in range(0, n, bs):
         b = min(n, a + bs)
         idxs = list(range(a, b))
@@ -33,7 +33,7 @@ def loader(n, boxes, ip, inx, bs):
         inps[:, 1, 0, 0, 0] -= 1
         inps[:, 2, 0, 0, 0] += 1
         inps.clamp_(0, n - 1)
-        yield (idxs, inps, None, None, None, None, None, boxes[a:b], boxes[a:b], ip[a:b], inx[a:b])
+        yield (idxs, inps, None, None, None if gt is None else gt[a:b], None, None, boxes[a:b], boxes[a:b], ip[a:b], inx[a:b])
 
 
 def cfg_opt(unc, flt):
@@ -60,11 +60,21 @@ def test_two_rounds_match_oracle(built_lib, unc, flt):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ref = O.score_pool(H, boxes, ip, inx, O.make_autoencoder(W), drop_ears=(unc == "WPU"))
+    # ground truth = the reference's predicted pose + noise, a few joints invisible, one item with none visible:
+    # the controller derives OKS (al_metric.py:42-69) and from it moks_queried (ActiveLearning.py:852-858)
+    rng = np.random.default_rng(7)
+    gt = ref["kpts"].reshape(n, 17, 3).astype(np.float32).copy()
+    gt[:, :, :2] += rng.normal(0, 6.0, (n, 17, 2)).astype(np.float32)
+    gt[:, :, 2] = (rng.random((n, 17)) < 0.8).astype(np.float32) * 2
+    gt[5, :, 2] = 0
+    oks_ref = {i: float(O.compute_oks(O.xyxy_to_xywh(boxes[i].tolist()), ref["kpts"][i].astype(np.float32).astype(np.float64),
+                                      gt[i].reshape(-1).astype(np.float64))) for i in range(n)}
     labeled, moks = [], 0.0
     for rnd in range(2):
-        al.eval_loader = loader(n, boxes, ip, inx, 64)
-        al.moks_queried = moks
+        al.eval_loader = loader(n, boxes, ip, inx, 64, gt)
+        assert np.isclose(al.moks_queried, moks, rtol=1e-6)
         al.eval_and_query()
+        assert np.allclose([al.OKS_dict[i] for i in range(n)], [oks_ref[i] for i in range(n)], rtol=1e-5, atol=1e-9)
         unl = [i for i in range(n) if i not in labeled]
         if unc == "THC+WPU":
             score = O.fuse_scores(ref["thc"][unl], ref["wpu"][unl], "const")
@@ -87,7 +97,8 @@ def test_two_rounds_match_oracle(built_lib, unc, flt):
             assert np.allclose([d[i][1] for i in range(n)], ref["wpu"], rtol=1e-5)
         labeled = labeled + expect
         assert al.labeled_id.index == labeled
-        moks = 0.6
+        moks = float(O.mean_oks_of_queries(expect, oks_ref))
+        assert np.isclose(al.moksQ_list[-1], moks, rtol=1e-6) and len(al.moksQ_list) == rnd + 1
         assert al.outcome() is None
 
 

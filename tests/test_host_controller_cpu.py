@@ -128,12 +128,18 @@ def _install_stand_ins(monkeypatch, v):
         w = torch.tensor(out, dtype=torch.float32)
         return (w, torch.zeros(len(out), dtype=torch.uint8)) if return_status else w
 
+    def oks(kpts, gt, bann):
+        n = kpts.shape[0]
+        out = [O.compute_oks(O.xyxy_to_xywh([float(x) for x in bann[i]]), kpts[i].reshape(-1).double().numpy(),
+                             gt[i].reshape(-1).double().numpy()) for i in range(n)]
+        return torch.tensor(out, dtype=torch.float64)
+
     def pack_ae_weights(weights, device):
         return [O.make_autoencoder(weights)], 42, 4
 
     for name, fn in dict(_flags=_flags, heatmap_scan=heatmap_scan, heatmap_entropy=heatmap_entropy,
                          pose_uncertainty=pose_uncertainty, cosine_rowsum=cosine_rowsum, minmax_f64=minmax_f64,
-                         blend_scores=blend_scores, fuse_scores=fuse_scores, coreset_select=coreset_select, wpu=wpu,
+                         blend_scores=blend_scores, fuse_scores=fuse_scores, coreset_select=coreset_select, wpu=wpu, oks=oks,
                          pack_ae_weights=pack_ae_weights).items():
         monkeypatch.setattr(ops, name, fn)
 

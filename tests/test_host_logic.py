@@ -124,7 +124,34 @@ def test_outcome_bookkeeping():
     al.labeled_id.update(range(20, 40)); al.unlabeled_id.difference_update(range(20, 40))
     assert al.outcome() is None and al.query_size == 160                           # last round: everything
     al.is_early_stop = True
-    assert isinstance(al.outcome(), dict)
+    al.percentage, al.uncertainty_mean, al.combine_weight, al.moksQ_list = [0.0], [1.5], [0.4], [0.7]
+    al.performance, al.performance_ann = [None], [None]
+    al.ospa_list, al.ospa_list_ann = [None], [None]
+    out = al.outcome()
+    # the reference's 20-tuple (ActiveLearning.py:203), per-round lists padded on early stop (:169-178)
+    assert isinstance(out, tuple) and len(out) == 20
+    assert out[0] is al.percentage and out[3] is al.query_list_list and out[19] is al.moksQ_list
+    assert len(al.performance) == len(cfg.VAL.QUERY_RATIO) + 1
+    assert len(al.uncertainty_mean) == len(al.moksQ_list) == len(al.combine_weight) == len(al.performance)
+    assert al.moksQ_list[-1] == 0.7 and out[14] == 100
+
+
+def test_oks_bookkeeping_sets_moks_and_early_stop():
+    """get_retrain_id / is_finished / get_corresponding_id on given per-item OKS values
+    (ActiveLearning.py:707-725, 852-884)."""
+    from vatlq import ActiveLearning
+    cfg, opt = _cfg_opt()
+    opt.retrain_thresh = 0.8
+    al = ActiveLearning(cfg, opt, eval_len=10)
+    al.labeled_id.update([0, 1]); al.unlabeled_id.difference_update([0, 1])
+    oks = {i: v for i, v in enumerate([0.95, 0.5, 0.9, 0.7, 0.85, 0.99, 0.6, 0.9, 0.9, 0.9])}
+    retrain, moks = al.get_retrain_id([3, 4], oks)
+    assert retrain == [1, 3, 4] and abs(moks - np.mean([0.85, 0.7])) < 1e-15
+    assert al.get_corresponding_id(oks, true=True, labeled=True) == [0]
+    assert al.get_corresponding_id(oks, true=False, labeled=False) == [3, 4, 6]   # 0.85 < 0.8 + 0.05 in binary
+    assert al.is_finished([3, 4], oks) == (100, 100, 100)
+    hi = {i: 0.9 for i in range(10)}
+    assert al.is_finished([3, 4], hi) == (20.0, 20.0, 20.0)
 
 
 def test_shard_ranges():

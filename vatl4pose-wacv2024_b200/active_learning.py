@@ -6,16 +6,17 @@ with the per-person Python loop replaced by batched CUDA kernels (ops.py / libva
 Everything else of the reference class (dataset building, estimator training, mAP/OSPA
 evaluation, plotting) is out of scope and is injected or hooked:
 
-    al = ActiveLearning(cfg, opt, model=estimator, eval_loader=loader, eval_len=len(dataset), AE=ae)
-    al.eval_and_query()          # fills labeled_id / unlabeled_id / query_list_list / ...
-    al.outcome()                 # bookkeeping of :166-205 without the retraining
+    al = ActiveLearning(cfg, opt)                       # builds estimator / loader / AE through the reference's builders
+    al = ActiveLearning(cfg, opt, model=estimator, eval_loader=loader, eval_len=len(dataset), AE=ae)   # or injected
+    al.eval_and_query()          # fills labeled_id / unlabeled_id / query_list_list / moks_queried / ...
+    al.outcome()                 # None while rounds remain, else the reference's 20-tuple (:203)
 
 Strategy names are the reference's (`opt.uncertainty`, `opt.representativeness`, `opt.filter`,
 ActiveLearning.py:329-401,467-481,533-619).  Uncertainties THC*, WPU*, THC+WPU, HP, TPC, Entropy
 and None, representativeness None / Influence / Random and filters None / Coreset / Diversity /
-Random run here; any other name (MPE, Margin, VL4Pose; weighted, K-Means) raises
-NotImplementedError naming the reference code path to use (dispatch to the reference, never a
-CPU re-implementation of ours).
+Random run here; names without a device path (see _require_accelerated) raise NotImplementedError
+naming the reference code path to use (dispatch to the reference, never a CPU re-implementation
+of ours).
 """
 from __future__ import annotations
 
@@ -200,7 +201,8 @@ def coreset_selection(self, embeddings, uncertainty):
 # the controller
 # ----------------------------------------------------------------------------------------
 
-_REFERENCE_ONLY_UNC = ("MPE", "VL4Pose", "Margin")     # need skimage.peak_local_max / the unfinished VL4Pose stub
+_REFERENCE_ONLY_UNC = ("VL4Pose",)                      # the reference's own VL4Pose branch is an unfinished stub (:390-391)
+_PEAK_UNC = ("MPE", "Margin")                           # skimage.peak_local_max based (:762-788)
 _SINGLE_UNC = ("HP", "TPC", "Entropy")
 
 
@@ -213,9 +215,10 @@ class ActiveLearning:
     (alphapose/datasets/posetrack21.py:207-) in pool order."""
 
     def __init__(self, cfg, opt, model=None, eval_loader=None, eval_len=None, AE=None, oks_fn=None,
-                 eval_hook=None, retrain_hook=None):
+                 eval_hook=None, retrain_hook=None, metrics_hook=None):
         self.round_cnt = 0
         self.cfg, self.opt = cfg, opt
+        self.one_by_one = bool(getattr(opt, "onebyone", False))
         self.strategy = opt.strategy
         self.uncertainty = opt.uncertainty
         self.representativeness = opt.representativeness
@@ -223,40 +226,87 @@ class ActiveLearning:
         self.video_id = getattr(opt, "video_id", None)
         self.get_prenext = getattr(opt, "get_prenext", ("THC" in self.uncertainty or self.uncertainty == "TPC"))
         self.model, self.eval_loader, self.AE = model, eval_loader, AE
-        self.oks_fn, self.eval_hook, self.retrain_hook = oks_fn, eval_hook, retrain_hook
+        self.oks_fn, self.eval_hook, self.retrain_hook, self.metrics_hook = oks_fn, eval_hook, retrain_hook, metrics_hook
         # dispatch keys: accept exactly the reference's names (:329-401,467-481,533-619)
         u = self.uncertainty
-        known = u in ("None", "THC+WPU") or "THC" in u or "WPU" in u or u in _REFERENCE_ONLY_UNC or u in _SINGLE_UNC
+        known = u in ("None", "THC+WPU") or "THC" in u or "WPU" in u or u in _REFERENCE_ONLY_UNC or u in _SINGLE_UNC \
+            or u in _PEAK_UNC
         if not known:
             raise ValueError("Uncertainty type is not supported")
         if self.representativeness not in ("None", "Influence", "Random"):
             raise ValueError("Representativeness type is not supported")
         if self.filter not in ("None", "weighted", "K-Means", "Coreset", "Diversity", "Random"):
             raise ValueError("Filter type is not supported")
+        if eval_len is None and eval_loader is None:
+            self._build_from_reference()          # the two-argument form of the reference (:52-164)
+            eval_loader = self.eval_loader
         self.eval_len = int(eval_len if eval_len is not None else len(eval_loader.dataset))
         self.query_ratio = cfg.VAL.QUERY_RATIO
         self.w_unc = cfg.VAL.W_UNC
         self.unc_lambda = cfg.VAL.UNC_LAMBDA
         self.query_sizes = [int(self.eval_len * x) for x in self.query_ratio]
         self.query_size = self.query_sizes[0]
-        if getattr(opt, "onebyone", False):
+        if self.one_by_one:
             self.query_size = 3
         self.unlabeled_id = IndexCollection(list(range(self.eval_len)))
         self.labeled_id = IndexCollection()
-        self.percentage, self.combine_weight = [], []
+        self.retrain_id = IndexCollection()
+        # result members of the reference (:121-137), same names, returned by outcome() (:203)
+        self.percentage, self.performance, self.performance_ann = [], [], []
+        self.ospa_list, self.ospa_list_ann, self.combine_weight = [], [], []
         self.query_list_list, self.uncertainty_dict, self.influence_dict = {}, {}, {}
-        self.uncertainty_mean, self.moksQ_list = [], []
-        self.moks_queried = 0
+        self.uncertainty_mean, self.spearmanr_list, self.corr_list, self.moksQ_list = [], [], [], []
+        self.true_labeled_dict, self.false_labeled_dict = {}, {}
+        self.true_unlabeled_dict, self.false_unlabeled_dict = {}, {}
+        # stopping criteria (:100-105)
         self.is_early_stop = False
+        self.finish_acc = float(getattr(opt, "retrain_thresh", 1.0))
+        self.finish_margin = 0.05
+        self.actual_finish = self.finished_minerror = self.finished_oursc = 100
+        self.moks_queried = 0
         self.eval_joints = list(range(ops.J))
         self.hm_size = cfg.DATA_PRESET.HEATMAP_SIZE
         self.coreset_batch = int(getattr(opt, "coreset_batch", 16))
         self.last_query = None
+        self.OKS_dict = None
+
+    def _build_from_reference(self):
+        """`ActiveLearning(cfg, opt)` exactly as scripts/Run_active_learning.py:165-173 calls it: the
+        evaluation dataset / loader, the estimator and the auto-encoder are built by the REFERENCE's
+        own builders (ActiveLearning.py:95-99,144-152; they stay reference code), which therefore must
+        be importable.  Everything after the estimator's forward runs here."""
+        try:
+            from alphapose.models import builder                      # noqa: F401  (reference package)
+        except Exception as exc:
+            raise _lib.VatlqError(
+                "ActiveLearning(cfg, opt) builds the dataset, the estimator and the auto-encoder through the "
+                "reference's builders (alphapose.models.builder): put the reference checkout on sys.path, or inject "
+                "model=, eval_loader=, eval_len= and AE= (see INTEGRATION.md)") from exc
+        cfg, opt = self.cfg, self.opt
+        ds = builder.build_dataset(cfg.DATASET.EVAL, preset_cfg=cfg.DATA_PRESET, train=False, get_prenext=self.get_prenext)
+        self.eval_dataset = ds
+        self.eval_loader = torch.utils.data.DataLoader(
+            ds, batch_size=cfg.VAL.BATCH_SIZE * getattr(opt, "num_gpu", 1), shuffle=False, num_workers=8, drop_last=False,
+            pin_memory=True, collate_fn=ds.my_collate_fn)                                           # (:97-99)
+        if self.model is None:
+            m = builder.build_sppe(cfg.MODEL, preset_cfg=cfg.DATA_PRESET)                           # (:213-221)
+            if not getattr(opt, "from_scratch", False):
+                if not cfg.MODEL.PRETRAINED:
+                    raise ValueError("No pretrained model is given!")
+                m.load_state_dict(torch.load(cfg.MODEL.PRETRAINED))
+            self.model = torch.nn.DataParallel(m, device_ids=getattr(opt, "gpus", None)).cuda()     # (:233)
+        if self.AE is None and "WPU" in self.strategy:                                              # (:150-152, 886-)
+            from active_learning.Whole_body_AE.AutoEncoder import WholeBodyAE as RefAE
+            ae = RefAE(z_dim=cfg.AE.Z_DIM)
+            pre = getattr(cfg.AE, "PRETRAINED", None)
+            if pre:
+                ae.load_state_dict(torch.load(pre))
+            self.AE = ae
 
     # -- dispatch guard: names this package does not accelerate stay on the reference ----
     def _require_accelerated(self):
         u = self.uncertainty
-        if u in _REFERENCE_ONLY_UNC:
+        if u in _REFERENCE_ONLY_UNC or (u in _PEAK_UNC and not hasattr(ops, "peak_uncertainty")):
             raise NotImplementedError(
                 f"uncertainty '{u}' is not on the accelerated path: run the reference's "
                 "ActiveLearning.eval_and_query (active_learning/ActiveLearning.py:329-401) for it")
@@ -271,10 +321,13 @@ class ActiveLearning:
         dev = _dev()
         n = self.eval_len
         use_wpu = "WPU" in self.uncertainty and self.uncertainty not in _SINGLE_UNC
-        want_feat = self.filter not in ("None", "Random")   # (:283)
+        # embeddings are collected when the filter OR the representativeness needs them (:283)
+        want_feat = self.filter not in ("None", "Random") or self.representativeness not in ("None", "Random")
         qp = QueryPass(n, dev, ae_weights=self.AE if use_wpu else None, uncertainty=self.uncertainty)
-        # the reference keeps an all-zero fvecs_matrix when no filter needs embeddings (:270,283)
-        X = torch.zeros((n, 2048), dtype=torch.float32, device=dev) if (want_feat or self.representativeness == "Influence") else None
+        # (the reference keeps an all-zero fvecs_matrix otherwise, :270)
+        X = torch.zeros((n, 2048), dtype=torch.float32, device=dev) if want_feat else None
+        oks_dev = torch.zeros(n, dtype=torch.float64, device=dev)
+        have_gt = True
         m = self.model
         if hasattr(m, "eval"):
             m.eval()
@@ -297,6 +350,15 @@ class ActiveLearning:
             ip = torch.as_tensor(np.asarray(isPrev)).to(torch.uint8)
             inx = torch.as_tensor(np.asarray(isNext)).to(torch.uint8)
             qp.score_chunk(pos, H, boxes, ip, inx)
+            # OKS of every item against its ground truth (:309, al_metric.py:42-69): the selection weights of
+            # the NEXT query (moks_queried) and the stopping criteria come from it
+            gt, bann = (batch[4], batch[8]) if len(batch) > 8 else (None, None)
+            if gt is not None and bann is not None and self.oks_fn is None:
+                gt_t = torch.as_tensor(np.asarray(gt), dtype=torch.float32).reshape(b, -1)
+                ba_t = torch.as_tensor(np.asarray(bann), dtype=torch.float32).reshape(b, 4)
+                oks_dev[pos:pos + b] = ops.oks(qp.kpts[pos:pos + b], gt_t, ba_t)
+            else:
+                have_gt = False
             if strict:   # the reference's own three forwards (:293-297)
                 Hp = m(inps[:, 1].to(dev))[:, self.eval_joints].float().contiguous()
                 Hn = m(inps[:, 2].to(dev))[:, self.eval_joints].float().contiguous()
@@ -308,6 +370,19 @@ class ActiveLearning:
             raise _lib.VatlqError(f"eval_loader produced {pos} items, expected {n}")
         if strict:
             qp.thc.copy_(thc_strict)
+        self.OKS_dict = None
+        self._strict_oks = True     # a full eval_and_query must be able to derive moks_queried (see _query)
+        if have_gt:
+            self.OKS_dict = dict(enumerate(oks_dev.cpu().tolist()))
+        if self.metrics_hook is not None:   # mAP / OSPA of :438-447 are evaluation (reference code): hooked
+            m_ = self.metrics_hook(self, qp.kpts) or {}
+            self.performance.append(m_.get("res"))
+            self.performance_ann.append(m_.get("res_ann"))
+            self.ospa_list.append(m_.get("ospa"))
+            self.ospa_list_ann.append(m_.get("ospa_ann"))
+        else:
+            for lst in (self.performance, self.performance_ann, self.ospa_list, self.ospa_list_ann):
+                lst.append(None)
         return self._query(qp, X)
 
     def _query(self, qp: QueryPass, X):
@@ -381,21 +456,88 @@ class ActiveLearning:
             self.coreset_stats = holder.coreset_stats
         self.last_query = SimpleNamespace(thc=qp.thc, wpu=qp.wpu, single=qp.aux, peak_mean=qp.peak_mean, kpts=qp.kpts,
                                           score=score, query_list=list(query_list))
-        if len(unl_idx) != 0:                                                          # (:629-637)
-            if self.oks_fn is not None:
-                oks = np.asarray(self.oks_fn(query_list, qp.kpts), dtype=np.float64)
-                self.moks_queried = float(np.mean(oks)) if oks.size else 0
+        OKS_dict = self.OKS_dict
+        if OKS_dict is None and self.oks_fn is not None:
+            OKS_dict = dict(enumerate(np.asarray(self.oks_fn(list(range(n)), qp.kpts), dtype=np.float64).tolist()))
+            self.OKS_dict = OKS_dict
+        if OKS_dict is not None:                                                       # (:620-627)
+            r = "Round" + str(self.round_cnt)
+            self.true_labeled_dict[r] = self.get_corresponding_id(OKS_dict, true=True, labeled=True)
+            self.true_unlabeled_dict[r] = self.get_corresponding_id(OKS_dict, true=True, labeled=False)
+            self.false_labeled_dict[r] = self.get_corresponding_id(OKS_dict, true=False, labeled=True)
+            self.false_unlabeled_dict[r] = self.get_corresponding_id(OKS_dict, true=False, labeled=False)
+        if len(unl_idx) != 0:                                                          # (:629-649)
+            if OKS_dict is None:
+                w_unc_rule = (self.filter == "Coreset" and self.uncertainty != "None" and self.cfg.VAL.UNC_LAMBDA != 0
+                              and not getattr(self.opt, "fixed_lambda", False))
+                if w_unc_rule and getattr(self, "_strict_oks", False):
+                    raise _lib.VatlqError(
+                        "the Coreset filter weighs distance against uncertainty with the mean OKS of the queried items "
+                        "(ActiveLearning.py:815-821,858): the loader must deliver GTkpts / bboxes_ann (batch[4], batch[8]) "
+                        "or an oks_fn must be given — without them moks_queried would silently stay 0")
                 self.moksQ_list.append(self.moks_queried)
+            else:
+                self.retrain_id = IndexCollection()
+                retrain_id, self.moks_queried = self.get_retrain_id(query_list, OKS_dict)
+                self.moksQ_list.append(self.moks_queried)
+                self.retrain_id.update(retrain_id)
             self.labeled_id.update(query_list)
             self.unlabeled_id.difference_update(query_list)
             self.query_list_list["Round" + str(self.round_cnt)] = list(map(int, query_list))
+            if OKS_dict is not None:
+                self.actual_finish, self.finished_minerror, self.finished_oursc = self.is_finished(query_list, OKS_dict)
+                if self.actual_finish < 100:
+                    self.is_early_stop = True                                          # (:646-649)
         return None
 
+    # ---- host bookkeeping on the per-item OKS values (tiny; ActiveLearning.py:707-725, 852-884) ----
+    def get_retrain_id(self, query_list, OKS_dict):
+        """ActiveLearning.get_retrain_id (:852-872): labelled items whose OKS is still low plus the new
+        queries; mOKS of the new queries (mean taken in descending-OKS order like the reference)."""
+        q = set(int(i) for i in query_list)
+        oks_q = sorted((OKS for idx, OKS in OKS_dict.items() if idx in q), reverse=True)
+        moks_queried = np.mean(oks_q)
+        retrain_id = [idx for idx, OKS in OKS_dict.items() if idx in self.labeled_id and OKS <= self.finish_acc + self.finish_margin]
+        retrain_id += list(query_list)
+        return retrain_id, moks_queried
+
+    def get_corresponding_id(self, OKS_dict, true=True, labeled=True):
+        """ActiveLearning.get_corresponding_id (:874-884)."""
+        thresh = self.finish_acc + self.finish_margin
+        pool = self.labeled_id if labeled else self.unlabeled_id
+        return [idx for idx, OKS in OKS_dict.items() if idx in pool and ((OKS >= thresh) if true else (OKS < thresh))]
+
+    def is_finished(self, query_list, OKS_dict):
+        """ActiveLearning.is_finished (:707-725): the three stopping criteria as label percentages."""
+        time = (len(self.labeled_id) / self.eval_len) * 100
+        vals = np.array(list(OKS_dict.values()))
+        if np.all(vals >= self.finish_acc) and time < self.actual_finish:
+            self.actual_finish = time
+        OKS_q = np.array([OKS_dict[int(i)] for i in query_list])
+        if np.mean(OKS_q) >= self.finish_acc and time < self.finished_minerror:
+            self.finished_minerror = time
+        OKS_lq = np.array([OKS_dict[int(i)] for i in self.labeled_id.index + list(query_list)])
+        if np.all(OKS_lq >= self.finish_acc) and time < self.finished_oursc:
+            self.finished_oursc = time
+        return self.actual_finish, self.finished_minerror, self.finished_oursc
+
     def outcome(self):
-        """Control flow of ActiveLearning.outcome (:166-205).  Retraining itself (:651-686) is the
-        caller's `retrain_hook(self)`.  Returns None while rounds remain; when finished, a dict
-        with the query-side members of the reference's 20-tuple (:203)."""
-        if self.is_early_stop or getattr(self.opt, "onebyone", False):
+        """ActiveLearning.outcome (:166-205).  Retraining itself (:651-686) is reference code behind
+        `retrain_hook(self)`.  Returns None while rounds remain; when finished, the reference's 20-tuple
+        (:203) — the evaluation members (performance, ospa) hold what `metrics_hook` delivered (None without)."""
+        if self.is_early_stop or self.one_by_one:
+            def last(lst):
+                return lst[-1] if lst else None
+            while len(self.performance) <= len(self.query_ratio):     # pad the remaining rounds (:169-178)
+                self.round_cnt += 1
+                self.performance.append(last(self.performance))
+                self.performance_ann.append(last(self.performance_ann))
+                self.ospa_list.append(last(self.ospa_list))
+                self.ospa_list_ann.append(last(self.ospa_list_ann))
+                self.uncertainty_mean.append(last(self.uncertainty_mean))
+                self.percentage.append(self.query_ratio[min(self.round_cnt, len(self.query_ratio)) - 1] * 100)
+                self.combine_weight.append(last(self.combine_weight))
+                self.moksQ_list.append(last(self.moksQ_list))
             finish = True
         else:
             if self.retrain_hook is not None:
@@ -412,7 +554,8 @@ class ActiveLearning:
                 finish = False
         if not finish:
             return None
-        return dict(percentage=self.percentage, query_list_list=self.query_list_list,
-                    uncertainty_dict=self.uncertainty_dict, uncertainty_mean=self.uncertainty_mean,
-                    influence_dict=self.influence_dict, combine_weight=self.combine_weight,
-                    moksQ_list=self.moksQ_list)
+        return (self.percentage, self.performance, self.performance_ann, self.query_list_list, self.uncertainty_dict,
+                self.uncertainty_mean, self.influence_dict, self.combine_weight, self.spearmanr_list, self.corr_list,
+                self.true_labeled_dict, self.true_unlabeled_dict, self.false_labeled_dict, self.false_unlabeled_dict,
+                self.actual_finish, self.finished_minerror, self.finished_oursc, self.ospa_list, self.ospa_list_ann,
+                self.moksQ_list)

@@ -68,7 +68,14 @@ struct Ctl {
   int emit_mode, target; // RankBlock::mode of that list; wanted candidates per round
   unsigned int filter_ticket, pairs_ticket;
   long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
+  // where a round's planning time goes (ns, %globaltimer; summed over the rounds of a call)
+  unsigned long long t_start, stat_ns_wait, stat_ns_tiles, stat_ns_plan;
 };
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct Best {
   double s;
@@ -1033,9 +1040,15 @@ __global__ void __launch_bounds__(kSeg * 32, 1) prune_filter_kernel(const float*
                                                                     const double* __restrict__ m, const double* __restrict__ xx,
                                                                     const long long* __restrict__ centers_all,
                                                                     const int* n_centers, int n_centers_imm, int center_off,
-                                                                    const PruneCtl* pc, unsigned char* __restrict__ seg_skip) {
+                                                                    const PruneCtl* pc, unsigned char* __restrict__ seg_skip,
+                                                                    size_t skip_stride) {
   __shared__ __align__(16) double s_part[2][kSeg][64];
   __shared__ double s_xxc[kB];
+  // blockIdx.y = centre group of the round: group y's flags are for the pass that applies centres
+  // [center_off + 8y, +8).  All groups are evaluated BEFORE the round's first pass: the max min_d a later
+  // group reads can only be larger than what its pass will see, so its flags are conservative (exact).
+  center_off += (int)blockIdx.y * kB;
+  seg_skip += (size_t)blockIdx.y * skip_stride;
   const int nb = min(kB, (n_centers ? *n_centers : n_centers_imm) - center_off);   // like pass_centers()
   if (nb <= 0) return;
   const long long* centers = centers_all + center_off;
@@ -1356,9 +1369,17 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctl->nb = 0;
     return;
   }
+  unsigned long long t0 = 0, t1 = 0;
+  const bool clocked = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  if (clocked) t0 = gtime_ns();
   if (mail != nullptr) {               // peer-memory exchange: the blocks of this round land in the local mailbox
     if (threadIdx.x == 0) wait_blocks(mail, ctl->world, seq);
     __syncthreads();
+  }
+  if (clocked) {
+    t1 = gtime_ns();
+    ctl->t_start = t1;
+    ctl->stat_ns_wait += t1 - t0;
   }
   {
     const int world = ctl->world;
@@ -1374,8 +1395,15 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (threadIdx.x == 0) ctl->pairs_ticket = 0;
+    unsigned long long t2 = 0;
+    if (threadIdx.x == 0) {
+      ctl->pairs_ticket = 0;
+      t2 = gtime_ns();
+      ctl->stat_ns_tiles += t2 - *((volatile unsigned long long*)&ctl->t_start);
+    }
     plan_body(blocks, send, Dcc, hist, out_idx, ctl);
+    __syncthreads();
+    if (threadIdx.x == 0) ctl->stat_ns_plan += gtime_ns() - t2;
   }
 }
 
@@ -1730,7 +1758,7 @@ struct Comm {
 // ---------------------------------------------------------------- workspace layout
 struct WsLayout {
   size_t xx, score, hist, partial, send, recv, dcc, ctl, dots, flags, total;
-  size_t prune, seg_of_row, seg_start, seg_r, seg_skip;   // pruning state (cd aliases dots during set-up)
+  size_t prune, seg_of_row, seg_start, seg_r, seg_skip, skip_stride;   // pruning state (cd aliases dots during set-up)
 };
 static WsLayout ws_layout(long long n, int world) {
   WsLayout L;
@@ -1754,7 +1782,8 @@ static WsLayout ws_layout(long long n, int world) {
   L.seg_of_row = take((size_t)n * 4);
   L.seg_start = take((size_t)(n + 1) * 4);
   L.seg_r = take((size_t)n * 8);
-  L.seg_skip = take((size_t)n);
+  L.seg_skip = take((size_t)n * (kMaxPicks / kB));   // one flag array per centre group of a round
+  L.skip_stride = align_up((size_t)n, 256);
   L.total = o;
   return L;
 }
@@ -1841,6 +1870,7 @@ struct PruneState {
   int* seg_start = nullptr;
   double* seg_r = nullptr;
   unsigned char* seg_skip = nullptr;
+  size_t skip_stride = 0;
   int filter_grid = 1;
 };
 static int prune_setup(PruneState& P, const float* X, const Geom& G, int64_t row_lo, int64_t row_hi, char* w,
@@ -1861,6 +1891,7 @@ static int prune_setup(PruneState& P, const float* X, const Geom& G, int64_t row
   P.seg_start = (int*)(w + L.seg_start);
   P.seg_r = (double*)(w + L.seg_r);
   P.seg_skip = (unsigned char*)(w + L.seg_skip);
+  P.skip_stride = L.skip_stride;
   const long long prune_min = g_prune_min_set >= 0 ? g_prune_min_set : prune_min_rows;
   P.mode = (G.d4 == kSeg * 4 * 16 && own >= prune_min && own >= 8 && own < (1LL << 30))
                ? (g_prune_mode_set >= 0 ? g_prune_mode_set : prune_env) : 0;
@@ -1877,10 +1908,13 @@ static int prune_setup(PruneState& P, const float* X, const Geom& G, int64_t row
   }
   return 0;
 }
-// flags for the pass that applies centers[center_off ..): launched right before that pass
-static int launch_filter(const PruneState& P, const PassArgs& a, cudaStream_t stream) {
-  prune_filter_kernel<16><<<P.filter_grid, kSeg * 32, 0, stream>>>(a.X, a.d4, a.lo, P.seg_start, P.seg_r, a.m, a.xx, a.centers,
-                                                                  a.n_centers, a.n_centers_imm, a.center_off, P.pc, P.seg_skip);
+// flags for the `groups` passes that apply centers[center_off + 8g ..), g = 0 .. groups-1 (flag array g):
+// ONE launch before the first of those passes
+static int launch_filter(const PruneState& P, const PassArgs& a, cudaStream_t stream, int groups = 1) {
+  dim3 grid((unsigned)P.filter_grid, (unsigned)groups);
+  prune_filter_kernel<16><<<grid, kSeg * 32, 0, stream>>>(a.X, a.d4, a.lo, P.seg_start, P.seg_r, a.m, a.xx, a.centers,
+                                                          a.n_centers, a.n_centers_imm, a.center_off, P.pc, P.seg_skip,
+                                                          P.skip_stride);
   VQ_LAUNCHED();
   return 0;
 }
@@ -2094,13 +2128,17 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         plan_kernel<<<1, kPlanThreads, 0, stream>>>(blocks, send, Dcc, hist, (long long*)out_idx, ctl);
         g_launches.fetch_add(1);
       }
+      if (prune_mode) {   // flags of every centre group of the round in one launch
+        PassArgs a{};
+        fill_pass(a);
+        rc = launch_filter(P, a, stream, (nbk + kB - 1) / kB);
+      }
       for (int off = 0; off < nbk && rc == 0; off += kB) {   // picks [off, off+8) of the round; the last pass emits
         PassArgs a{};
         fill_pass(a);
         a.center_off = off;
+        if (prune_mode) a.seg_skip = P.seg_skip + (size_t)(off / kB) * P.skip_stride;
         a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
-        if (prune_mode) rc = launch_filter(P, a, stream);
-        if (rc) break;
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
         rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
@@ -2161,6 +2199,9 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     host_stats[5] = hc->stat_cand_sum;
     host_stats[6] = rounds_done;
     host_stats[7] = nbk;
+    host_stats[8] = (int64_t)hc->stat_ns_wait;
+    host_stats[9] = (int64_t)hc->stat_ns_tiles;
+    host_stats[10] = (int64_t)hc->stat_ns_plan;
   }
   cudaFreeHost(h_picked);
   return rc;

@@ -208,6 +208,9 @@ class CoresetStats:
     candidates: int
     rounds_launched: int
     batch: int
+    ns_wait: int = 0        # waiting for the peers' candidate blocks (summed over the rounds)
+    ns_tiles: int = 0       # candidate x candidate distance tiles
+    ns_plan: int = 0        # the planner (greedy replay on the candidates)
 
 
 def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: float, lam: float,
@@ -232,7 +235,7 @@ def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: fl
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     min_d = torch.empty(n, dtype=torch.float64, device=dev)
     out = torch.empty(max(k, 1), dtype=torch.int64, device=dev)
-    stats = (C.c_int64 * 8)()
+    stats = (C.c_int64 * 16)()
     with torch.cuda.device(dev):
         _lib.check(L.vatlq_coreset_init(_ptr(X), n, d, lo, hi, _ptr(lab) if lab.numel() else None, lab.numel(),
                                         _ptr(min_d), _ptr(ws), ws_bytes, _stream()), "vatlq_coreset_init")
@@ -241,7 +244,7 @@ def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: fl
                                           C.c_void_p(comm) if comm else None, _ptr(ws), ws_bytes,
                                           C.cast(stats, C.c_void_p), _stream()), "vatlq_coreset_select")
     picks = out[:k]
-    st = CoresetStats(*[int(v) for v in stats])
+    st = CoresetStats(*[int(v) for v in stats][:11])
     if return_state:
         return picks, st, min_d, unc
     return picks, st
@@ -383,4 +386,20 @@ def blend_scores(unc: torch.Tensor, infl: torch.Tensor, combine_weight: float, m
     with torch.cuda.device(unc.device):
         _lib.check(_lib.lib().vatlq_fuse_blend(_ptr(unc), _ptr(infl), _ptr(mk), n, float(combine_weight), _ptr(out), _stream()),
                    "vatlq_fuse_blend")
+    return out
+
+
+def oks(kpts: torch.Tensor, gt_kpts: torch.Tensor, bbox_ann_xyxy: torch.Tensor) -> torch.Tensor:
+    """OKS of every predicted pose against its ground truth (al_metric.py:42-69; call site
+    ActiveLearning.py:309), fp64 (n,).  kpts / gt_kpts (n,17,3) fp32, bbox_ann (n,4) xyxy fp32."""
+    kpts = _cuda(kpts, torch.float32, "kpts")
+    n = kpts.shape[0]
+    dev = kpts.device
+    gt = _cuda(gt_kpts.to(dev).reshape(n, -1), torch.float32, "gt_kpts")
+    bb = _cuda(bbox_ann_xyxy.to(dev).reshape(n, 4), torch.float32, "bbox_ann_xyxy")
+    if kpts.numel() != n * 51 or gt.numel() != n * 51:
+        raise _lib.VatlqError("kpts and gt_kpts must be (n,17,3)")
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vatlq_oks(_ptr(kpts), _ptr(gt), _ptr(bb), n, _ptr(out), _stream()), "vatlq_oks")
     return out

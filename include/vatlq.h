@@ -153,6 +153,22 @@ int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t row_lo, int64
                          int64_t* out_idx, void* comm,
                          void* ws, size_t ws_bytes, int64_t* host_stats, vatlq_stream_t stream);
 
+/* Labelled-set initialisation on the 5th-generation tensor cores (d == 2048): same result as
+ * vatlq_coreset_init — min_d[i] = min over the labelled rows of the canonical fp64 distance, bit for bit —
+ * but the N x L contraction runs as a TF32 tcgen05.mma GEMM (2-D TMA loads, fp32 accumulators in TMEM) whose
+ * result, with a proved error bound, only decides WHICH (row, centre) pairs can be the minimum; those are
+ * re-scored with the canonical fp64 arithmetic (csrc/tc_dist.cu).  Replaces sklearn's N x L distance matrix
+ * of ActiveLearning.py:802-814,841.  ws from vatlq_coreset_init_tc_workspace_bytes(n, row_hi-row_lo, n_labeled).
+ * flags & 1: also check a sample of the TF32 values against the bound (host_stats4[2] must stay 0).
+ * host_stats4 = {pairs listed, pair capacity, bound violations, centre groups}; tmin_out (optional, fp32
+ * [row_hi-row_lo]): the approximate minimum squared distance per row.  Returns VATLQ_ESTATE when the
+ * candidate list overflows (call vatlq_coreset_init instead).  The call synchronises the stream. */
+size_t vatlq_coreset_init_tc_workspace_bytes(int64_t n, int64_t n_owned, int64_t n_labeled);
+int vatlq_coreset_init_tc(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
+                          const int64_t* labeled, int64_t n_labeled, double* min_d,
+                          void* ws, size_t ws_bytes, int flags, int64_t* host_stats4, float* tmin_out,
+                          vatlq_stream_t stream);
+
 /* Exact pruning of the passes over X (d == 2048, >= VATLQ_PRUNE_MIN_ROWS owned rows, default 8192):
  * consecutive rows of an id-sorted pool are near each other, so the owned rows are cut into segments
  * with an anchor row and a radius, and a pass does not stream the 8-row tiles whose segments

@@ -186,7 +186,44 @@ def pin_next_rows(R, O, synth):
     np.savez_compressed(os.path.join(GOLD, "next.npz"), **out)
 
 
+def pin_oks(R, O, synth):
+    """OKS (active_learning/al_metric.py:42-69, call site ActiveLearning.py:309) and the mOKS of a query list
+    (get_retrain_id, :852-858): the reference's functions on seeded poses, incl. the no-visible-joint branch."""
+    from active_learning.al_metric import compute_OKS
+    rng = np.random.default_rng(17)
+    n = 96
+    kp, bb = synth.poses(n, seed=3)
+    gt = kp.copy()
+    gt[:, :, :2] += rng.normal(0, 8.0, (n, 17, 2)).astype(np.float32)
+    gt[:, :, 2] = (rng.random((n, 17)) < 0.75).astype(np.float32) * 2
+    gt[3, :, 2] = 0                      # nothing visible: distance to the doubled box
+    gt[4, :, 2] = 0; kp[4, :, 0] += 900   # ... with predictions far outside it
+    gt[7] = kp[7]; gt[7, :, 2] = 1       # perfect prediction -> 1.0
+    ref = []
+    for i in range(n):
+        box = R.bbox_xyxy_to_xywh(bb[i].tolist())
+        k = kp[i].reshape(-1).tolist()
+        g = gt[i].reshape(-1).tolist()
+        ref.append(float(compute_OKS(box, k, g)))
+        same(ref[-1], float(O.compute_oks(O.xyxy_to_xywh(bb[i].tolist()), k, g)), f"oks {i}")
+    oks_dict = dict(enumerate(ref))
+    q = sorted(rng.choice(n, 20, replace=False).tolist())
+    fake = SimpleNamespace(labeled_id=R.IndexCollection([1, 2, 3]), unlabeled_id=R.IndexCollection(list(range(4, n))),
+                           finish_acc=0.8, finish_margin=0.05)
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        retrain_ref, moks_ref = R.AL.get_retrain_id(fake, q, oks_dict)
+    same(moks_ref, O.mean_oks_of_queries(q, oks_dict), "mOKS of the queries")
+    np.savez_compressed(os.path.join(GOLD, "oks.npz"), kpts=kp, gt=gt, boxes=bb, oks=np.array(ref), query=np.array(q, np.int64),
+                        moks=np.float64(moks_ref), retrain=np.array(retrain_ref, np.int64))
+    print("OKS pinned:", len(ref), "items, mOKS", moks_ref)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "oks":     # only the OKS fixture (the others are unchanged)
+        from oracle import vatl_oracle as O
+        pin_oks(import_reference(), O, importlib.import_module("vatl4pose-wacv2024_b200.synth"))
+        return
     from oracle import vatl_oracle as O
     synth = importlib.import_module("vatl4pose-wacv2024_b200.synth")
     R = import_reference()
@@ -334,6 +371,7 @@ def main():
             flat[f"{tag}/{key}"] = np.asarray(val)
     np.savez_compressed(os.path.join(GOLD, "coreset.npz"), **flat)
     pin_next_rows(R, O, synth)
+    pin_oks(R, O, synth)
     print("oracle pinned against the reference; fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(f"  {fn}: {os.path.getsize(os.path.join(GOLD, fn)) / 1e6:.2f} MB")

@@ -76,3 +76,14 @@ def test_golden_fusion_bit_exact(built_lib, gold_fuse):
         assert (out[~sel] == 0).all()
     single = v.ops.fuse_scores(torch.from_numpy(t32).cuda(), None, None).cpu().numpy()
     assert np.array_equal(single, O.fuse_scores(t32.astype(np.float64)))
+
+
+def test_oks_matches_reference_golden(built_lib):
+    """vatlq_oks against al_metric.compute_OKS outputs (fp64; exp differs from libm by <= 1 ulp)."""
+    import torch
+    from conftest import load_golden
+    z = load_golden("oks.npz")
+    got = built_lib.ops.oks(torch.from_numpy(z["kpts"]).cuda(), torch.from_numpy(z["gt"]).cuda(),
+                            torch.from_numpy(z["boxes"]).cuda()).cpu().numpy()
+    assert np.allclose(got, z["oks"], rtol=1e-12, atol=1e-300)
+    assert got[7] == 1.0

@@ -117,3 +117,15 @@ def test_influence_diversity_topk_match_reference(gold_next):
         assert O.topk_select(unl, total, k) == g[f"{tag}_topk"].tolist()
         assert O.diversity_select(X, unl, total, k) == g[f"{tag}_diversity"].tolist()
     assert O.influence_scores(np.zeros((3, 8)), [1]).tolist() == [0.0]
+
+
+def test_oks_oracle_matches_reference_golden():
+    """al_metric.compute_OKS / get_retrain_id's mOKS (reference outputs in tests/golden/oks.npz)."""
+    from conftest import load_golden
+    from oracle import vatl_oracle as O
+    z = load_golden("oks.npz")
+    got = [O.compute_oks(O.xyxy_to_xywh(z["boxes"][i].tolist()), z["kpts"][i].reshape(-1).tolist(), z["gt"][i].reshape(-1).tolist())
+           for i in range(len(z["oks"]))]
+    assert np.array_equal(np.array(got), z["oks"])
+    assert z["oks"][7] == 1.0 and z["oks"][4] < 1e-3
+    assert O.mean_oks_of_queries(z["query"].tolist(), dict(enumerate(z["oks"].tolist()))) == float(z["moks"])

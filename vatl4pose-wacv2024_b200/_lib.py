@@ -26,6 +26,8 @@ SIGNATURES = {
     "vatlq_fuse_final": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "vatlq_coreset_workspace_bytes": (_sz, [_i64, _int, _int]),
     "vatlq_coreset_init": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vatlq_coreset_init_tc_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "vatlq_coreset_init_tc": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _int, _vp, _vp, _vp]),
     "vatlq_coreset_select": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _dbl, _dbl, _i64,
                                     _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vatlq_coreset_prune_stats": (_int, [_vp, _int]),
@@ -49,6 +51,7 @@ SIGNATURES = {
 }
 
 _lib = None
+EINVAL, ECOMM, ESTATE = -1, -3, -4     # VATLQ_E* of include/vatlq.h
 
 
 class VatlqError(RuntimeError):

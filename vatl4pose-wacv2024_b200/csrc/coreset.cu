@@ -339,7 +339,10 @@ struct PassArgs {
   double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
   // exact pruning (fast path only, see "pruning" below): tiles whose segments were all flagged by
   // prune_filter_kernel are not streamed; their rows keep min_d and only take part in the epilogue
+  int only_if_le8;           // solo pass of a 16-pick round: run only when the round planned <= 8 picks (else the
+                             // paired pass applies all of them in ONE read of X)
   const int* seg_of_row;             // [owned row] -> segment id, or null
+  size_t skip_stride;                // paired pass: the flags of centre group 1 start at seg_skip + skip_stride
   const unsigned char* seg_skip;     // [segment] 1: no row of the segment can get closer to this pass's centres
   int prune_mode;                    // 0 off, 1 skip, 2 verify (stream everything, count rows that changed anyway)
   unsigned long long* prune_stats;   // [0] tiles seen, [1] tiles streamed, [2] verify violations
@@ -636,15 +639,16 @@ __device__ __forceinline__ ApplyConst apply_const(const PassArgs& a, bool final_
 }
 // tile_mode: 0 streamed, 1 pruned (no dot products were computed: min_d stays), 2 verify (streamed
 // although the filter flagged it: count the rows whose min_d moved anyway — must stay 0)
+template <int NC = kB>
 __device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c, long long i, const double* s_xxc,
                                           const long long* s_pick, unsigned int* s_hist, Best& best, int tile_mode = 0) {
-  const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * kB);
+  const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * NC);
   const double xxi = a.xx[i];
   double tm = INFINITY;
   bool picked = false;
   if (tile_mode != 1) {
 #pragma unroll
-    for (int q = 0; q < kB / 2; ++q) {
+    for (int q = 0; q < NC / 2; ++q) {
       const double2 d2 = __ldcg(dp + q);
       tm = fmin(tm, sq_from_dot(d2.x, xxi, s_xxc[2 * q]));
       tm = fmin(tm, sq_from_dot(d2.y, xxi, s_xxc[2 * q + 1]));
@@ -699,7 +703,7 @@ constexpr int kStageBytesX = 8 * kRowBytesX;               // 66 048
 constexpr int kWsThreads = (kSeg + 4) * 32;                // 8 compute warps + producer + 3 epilogue warps
 constexpr int kMaxTilesCta = 2048;                         // tiles per CTA the pruned-tile list can hold
 constexpr size_t kWsSmem = (size_t)kStagesX * kStageBytesX + sizeof(double) * kPartBufs * kSeg * 64 + 2 * kStagesX * 8 +
-                           kB * 16 + (kNB + 1) * 4 + 128 + kMaxTilesCta * 2 + kMaxTilesCta / 8 + 16;
+                           2 * kB * 16 + (kNB + 1) * 4 + 128 + kMaxTilesCta * 2 + kMaxTilesCta / 8 + 16;
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void named_sync(int id, int count) {
@@ -714,34 +718,63 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
   return r;
 }
 
-template <int STEPS>
+// PAIR = true ("paired pass"): the grid is launched as clusters of two CTAs (one TPC).  Both CTAs of a pair walk the
+// SAME tile sequence, CTA r holding centre group r (picks 8r .. 8r+7) as its register-resident B operands, so a round
+// of up to 16 picks reads X from HBM ONCE: the pair's two TMA requests for a tile arrive at the L2 together and
+// are served by one DRAM fetch.  The cluster only provides co-scheduling and the barrier between the tile loop and the
+// row finishing (each CTA finishes half of the pair's rows from both CTAs' dot products, 16 per row).
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int STEPS, bool PAIR>
 __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   static_assert(STEPS * 16 * kSeg * 4 + 64 == kRowBytesX, "stage geometry is for d = 2048");
+  constexpr int NC = PAIR ? 2 * kB : kB;          // dot products per row the finishing reads
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* stage0 = smem_raw;
   double (*s_part)[kSeg][64] = reinterpret_cast<double (*)[kSeg][64]>(smem_raw + (size_t)kStagesX * kStageBytesX);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_part + kPartBufs);
   uint64_t* empty = full + kStagesX;
   double* s_xxc = reinterpret_cast<double*>(empty + kStagesX);
-  long long* s_pick = reinterpret_cast<long long*>(s_xxc + kB);
-  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + kB);
+  long long* s_pick = reinterpret_cast<long long*>(s_xxc + 2 * kB);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_pick + 2 * kB);
   // pruning: the tiles this CTA streams (indices k into its own tile sequence), a bitmap of the
   // flagged ones, and the number of streamed tiles
   unsigned short* s_tiles = reinterpret_cast<unsigned short*>(s_hist + (kNB + 1) + 3);
   unsigned int* s_flagged = reinterpret_cast<unsigned int*>(s_tiles + kMaxTilesCta);
   int* s_na = reinterpret_cast<int*>(s_flagged + kMaxTilesCta / 32);
 
+  const int total = a.n_centers ? *a.n_centers : a.n_centers_imm;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
   bool final_pass;
-  const int nb = pass_centers(a, final_pass);
-  if (nb <= 0) return;
-  const long long* centers = a.centers + a.center_off;
+  int nb;
+  if (PAIR) {
+    if (total <= kB) return;                       // (both CTAs of the pair: the solo pass handles short rounds)
+    nb = min(kB, total - kB * crank);
+    final_pass = true;
+  } else {
+    if (a.only_if_le8 && total > kB) return;
+    nb = pass_centers(a, final_pass);
+    if (nb <= 0) return;
+  }
+  const long long* centers = a.centers + a.center_off + kB * crank;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncl = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;       // independent tile walkers
+  const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.ctl) a.ctl->stat_passes += 1;
     if (a.did_work) *a.did_work = 1;
   }
-  if (threadIdx.x < kB) {
-    const long long p = centers[min((int)threadIdx.x, nb - 1)];   // pad with the last centre: min() is idempotent
+  if (threadIdx.x < NC) {
+    // every centre the finishing sees (padded with the last one: min() is idempotent)
+    const int last = PAIR ? total - 1 : nb - 1;
+    const long long p = (a.centers + a.center_off)[min((int)threadIdx.x, last)];
     s_xxc[threadIdx.x] = a.xx[p];
     s_pick[threadIdx.x] = p;
   }
@@ -754,8 +787,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const long long ntiles = (a.hi - a.lo + 7) / 8;
-  const int nt = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  // tile j of the streamed sequence is tile k = tile_of(j) of the CTA (rows (blockIdx.x + k*gridDim.x)*8 ...)
+  const int nt = ((long long)cid < ntiles) ? (int)((ntiles - cid + ncl - 1) / ncl) : 0;
+  // tile j of the streamed sequence is tile k = tile_of(j) of the walker (rows (cid + k*ncl)*8 ...)
   const bool use_list = a.seg_skip != nullptr && a.prune_mode != 0 && nt <= kMaxTilesCta;
   if (warp == kSeg + 1) {
     int na = 0;
@@ -764,11 +797,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
         const int k = base + lane;
         bool flagged = false;
         if (k < nt) {
-          const long long r0 = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8;   // relative to a.lo
+          const long long r0 = ((long long)cid + (long long)k * ncl) * 8;   // relative to a.lo
           const long long r1 = min(r0 + 7, a.hi - a.lo - 1);
           const int s0 = a.seg_of_row[r0], s1 = a.seg_of_row[r1];
           flagged = true;
-          for (int sg = s0; sg <= s1; ++sg) flagged = flagged && (a.seg_skip[sg] != 0);
+          for (int sg = s0; sg <= s1; ++sg) {
+            flagged = flagged && (a.seg_skip[sg] != 0);
+            if (PAIR) flagged = flagged && (a.seg_skip[a.skip_stride + sg] != 0);   // ... for BOTH centre groups
+          }
         }
         const unsigned fm = __ballot_sync(0xffffffffu, flagged);
         if (lane == 0) s_flagged[base >> 5] = fm;
@@ -782,7 +818,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     }
     if (lane == 0) {
       *s_na = na;
-      if (a.prune_stats && nt > 0) {
+      if (a.prune_stats && nt > 0 && crank == 0) {
         atomicAdd(&a.prune_stats[0], (unsigned long long)nt);
         atomicAdd(&a.prune_stats[1], (unsigned long long)na);
       }
@@ -855,7 +891,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
         if (lane == 0) mbar_expect_tx(&full[st], 8u * 2048u * 4u);
         __syncwarp();
         if (lane < 8) {
-          const long long row = min(a.lo + ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + lane, a.hi - 1);
+          const long long row = min(a.lo + ((long long)cid + (long long)k * ncl) * 8 + lane, a.hi - 1);
           tma_load_1d(stage0 + (size_t)st * kStageBytesX + lane * kRowBytesX, a.X + (size_t)row * 2048, 2048u * 4u, &full[st]);
         }
         if (++st == kStagesX) {
@@ -873,22 +909,27 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
         const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
         const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
         if (j + kPartBufs < na) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
-        const long long row = ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + r;   // relative to a.lo
-        if (a.lo + row < a.hi) *reinterpret_cast<double2*>(a.dots + row * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
+        const long long row = ((long long)cid + (long long)k * ncl) * 8 + r;   // relative to a.lo
+        if (a.lo + row < a.hi)
+          *reinterpret_cast<double2*>(a.dots + row * NC + crank * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
       }
+      if (PAIR) __threadfence();                  // the partner CTA reads these dot products
     }
   }
-  // ---- apply phase: the CTA's own rows (their dot products were written by its own epilogue
-  // warps, visible after the barrier), one row per compute-warpgroup thread at a time
+  // ---- apply phase: the walker's own rows (their dot products were written by its own epilogue
+  // warps, visible after the barrier), one row per compute-warpgroup thread at a time; a pair splits
+  // its rows by tile parity after the cluster barrier that makes both CTAs' dot products visible
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   Best best{-INFINITY, 0x7fffffffffffffffLL};
   const ApplyConst ac = apply_const(a, final_pass);
   if (warp < kSeg) {
     for (int q = threadIdx.x; q < nt * 8; q += kSeg * 32) {
       const int k = q >> 3;
-      const long long i = a.lo + ((long long)blockIdx.x + (long long)k * gridDim.x) * 8 + (q & 7);
+      if (PAIR && (k & 1) != crank) continue;
+      const long long i = a.lo + ((long long)cid + (long long)k * ncl) * 8 + (q & 7);
       const int tile_mode = (use_list && ((s_flagged[k >> 5] >> (k & 31)) & 1u)) ? a.prune_mode : 0;
-      if (i < a.hi) apply_row(a, ac, i, s_xxc, s_pick, s_hist, best, tile_mode);
+      if (i < a.hi) apply_row<NC>(a, ac, i, s_xxc, s_pick, s_hist, best, tile_mode);
     }
   }
   __syncthreads();
@@ -1776,7 +1817,7 @@ static WsLayout ws_layout(long long n, int world) {
   L.send = take(sizeof(RankBlock));
   L.recv = take(sizeof(RankBlock) * (size_t)kMaxRanks);
   L.dcc = take((size_t)kCap * kCap * 8);
-  L.dots = take((size_t)n * kB * 8);
+  L.dots = take((size_t)n * 2 * kB * 8);   // up to 16 dot products per owned row (paired pass)
   L.flags = take(1024);
   L.prune = take(sizeof(PruneCtl));
   L.seg_of_row = take((size_t)n * 4);
@@ -1844,17 +1885,70 @@ static int launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream
   return 0;
 }
 
-static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+static int configure_pass() {
   static bool configured = false;
   if (!configured) {
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
+    VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
     configured = true;
   }
+  return 0;
+}
+
+// CTAs of the paired pass: the largest even count whose clusters of two are all co-resident (0: clusters unavailable)
+static int pair_grid() {
+  static int grid = -1;
+  if (grid < 0) {
+    grid = 0;
+    if (const char* e = getenv("VATLQ_PAIR"))
+      if (!strcmp(e, "0") || !strcmp(e, "off")) return grid;
+    if (configure_pass() != 0) return grid;   // (the occupancy query needs the opt-in shared-memory size)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sm_count() & ~1));
+    cfg.blockDim = dim3(kWsThreads);
+    cfg.dynamicSmemBytes = kWsSmem;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, pass_kernel_tma<16, true>, &cfg) == cudaSuccess && ncl > 0)
+      grid = 2 * std::min(ncl, sm_count() / 2);
+    cudaGetLastError();
+  }
+  return grid;
+}
+
+// the paired pass of a 16-pick round (d = 2048 only): applies picks [0, nb) when nb > 8, reading X once
+static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+  if (int e = configure_pass()) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)pair_grid());
+  cfg.blockDim = dim3(kWsThreads);
+  cfg.dynamicSmemBytes = kWsSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2;
+  at.val.clusterDim.y = at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  if (ev0) cudaEventRecord(ev0, stream);
+  VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true>, a));
+  if (ev1) cudaEventRecord(ev1, stream);
+  VQ_LAUNCHED();
+  return 0;
+}
+
+static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+  if (int e = configure_pass()) return e;
   if (ev0) cudaEventRecord(ev0, stream);
   const bool fast = a.d4 == kSeg * 4 * 16 && a.dots != nullptr;   // d = 2048
-  if (fast) pass_kernel_tma<16><<<sm_count(), kWsThreads, kWsSmem, stream>>>(a);
+  if (fast) pass_kernel_tma<16, false><<<sm_count(), kWsThreads, kWsSmem, stream>>>(a);
   else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   if (ev1) cudaEventRecord(ev1, stream);
@@ -1928,6 +2022,10 @@ static void prune_collect(const PruneState& P) {
     g_prune[3] = hp.nseg;
   }
 }
+
+namespace vatlq {
+int vq_launch_norms(const float* X, int64_t n, int d, double* xx, cudaStream_t stream) { return launch_norms(X, n, d, xx, stream); }
+}  // namespace vatlq
 
 extern "C" int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,
                                   const int64_t* labeled, int64_t n_labeled, double* min_d, void* ws,
@@ -2044,6 +2142,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   VQ_REQUIRE(fgrid <= 4096 && sm_count() <= 4096, "grid too large for the arg-max scratch");
   const size_t pairs_smem = G.smem;
   const bool fast_d = (G.d4 == kSeg * 4 * 16);   // d = 2048: register-resident centres
+  const bool use_pair = fast_d && nbk > kB && pair_grid() >= 2;   // 16 picks per round in one read of X
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -2133,16 +2232,37 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         fill_pass(a);
         rc = launch_filter(P, a, stream, (nbk + kB - 1) / kB);
       }
-      for (int off = 0; off < nbk && rc == 0; off += kB) {   // picks [off, off+8) of the round; the last pass emits
-        PassArgs a{};
-        fill_pass(a);
-        a.center_off = off;
-        if (prune_mode) a.seg_skip = P.seg_skip + (size_t)(off / kB) * P.skip_stride;
-        a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
+      auto timed_launch = [&](PassArgs& a, bool pair) {
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
-        rc = timed ? launch_pass(a, stream, g_prof.ev[g_prof.used], g_prof.ev[g_prof.used + 1]) : launch_pass(a, stream);
+        cudaEvent_t e0 = timed ? g_prof.ev[g_prof.used] : nullptr, e1 = timed ? g_prof.ev[g_prof.used + 1] : nullptr;
+        const int r = pair ? launch_pass_pair(a, stream, e0, e1) : launch_pass(a, stream, e0, e1);
         if (timed) g_prof.used += 2;
+        return r;
+      };
+      if (use_pair && rc == 0) {
+        // a round of 9..16 picks is applied by ONE paired pass (X read once); a shorter round by the solo pass
+        PassArgs a{};
+        fill_pass(a);
+        a.skip_stride = P.skip_stride;
+        a.push = push_of(seq0 + round_no + 1);   // the block this round's (only) pass publishes
+        rc = timed_launch(a, true);
+        if (rc == 0) {
+          PassArgs b{};
+          fill_pass(b);
+          b.only_if_le8 = 1;
+          b.push = push_of(seq0 + round_no + 1);
+          rc = timed_launch(b, false);
+        }
+      } else {
+        for (int off = 0; off < nbk && rc == 0; off += kB) {   // picks [off, off+8) of the round; the last pass emits
+          PassArgs a{};
+          fill_pass(a);
+          a.center_off = off;
+          if (prune_mode) a.seg_skip = P.seg_skip + (size_t)(off / kB) * P.skip_stride;
+          a.push = push_of(seq0 + round_no + 1);   // the block this round's final pass publishes
+          rc = timed_launch(a, false);
+        }
       }
     }
     if (rc) break;

@@ -7,6 +7,7 @@ falls back: a missing library or a non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -213,9 +214,37 @@ class CoresetStats:
     ns_plan: int = 0        # the planner (greedy replay on the candidates)
 
 
+TC_INIT_MIN_LABELED = 256     # below this the exact passes are cheaper than two GEMM sweeps
+_tc_init_stats = {"calls": 0, "fallbacks": 0, "pairs": 0, "violations": 0}
+
+
+def coreset_init_tc(X: torch.Tensor, lab: torch.Tensor, min_d: torch.Tensor, lo: int, hi: int, verify: bool = False,
+                    want_tmin: bool = False):
+    """min_d[lo:hi] = distance to the nearest labelled row through the TF32 tcgen05 GEMM + exact re-scoring
+    (vatlq_coreset_init_tc).  Returns (ok, stats dict, tmin or None); ok False = candidate list overflow."""
+    n, d = X.shape
+    L = _lib.lib()
+    ws_bytes = L.vatlq_coreset_init_tc_workspace_bytes(n, hi - lo, lab.numel())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    st = (C.c_int64 * 4)()
+    tmin = torch.empty(hi - lo, dtype=torch.float32, device=X.device) if want_tmin else None
+    with torch.cuda.device(X.device):
+        rc = L.vatlq_coreset_init_tc(_ptr(X), n, d, lo, hi, _ptr(lab), lab.numel(), _ptr(min_d), _ptr(ws), ws_bytes,
+                                     1 if verify else 0, C.cast(st, C.c_void_p), _ptr(tmin), _stream())
+    stats = {"pairs": int(st[0]), "capacity": int(st[1]), "violations": int(st[2]), "groups": int(st[3])}
+    _tc_init_stats["calls"] += 1
+    _tc_init_stats["pairs"] += stats["pairs"]
+    _tc_init_stats["violations"] += stats["violations"]
+    if rc == _lib.ESTATE:
+        _tc_init_stats["fallbacks"] += 1
+        return False, stats, tmin
+    _lib.check(rc, "vatlq_coreset_init_tc")
+    return True, stats, tmin
+
+
 def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: float, lam: float,
                    rule: str = "w_unc", first_pick: int = -1, batch: int = 16, comm=None,
-                   row_range: tuple[int, int] | None = None, return_state: bool = False):
+                   row_range: tuple[int, int] | None = None, return_state: bool = False, tc_init: bool | None = None):
     """k-center greedy selection (vatlq_coreset_init + vatlq_coreset_select).
     X (n,d) fp32 CUDA (replicated on every rank when comm is given), unc (n,) fp64 CUDA — a
     private copy is made, like the caller's deepcopy at ActiveLearning.py:612-613.
@@ -236,9 +265,15 @@ def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: fl
     min_d = torch.empty(n, dtype=torch.float64, device=dev)
     out = torch.empty(max(k, 1), dtype=torch.int64, device=dev)
     stats = (C.c_int64 * 16)()
+    if tc_init is None:    # the labelled-set contraction on the tcgen05 tensor cores when it is large enough to pay
+        tc_init = d == 2048 and lab.numel() >= TC_INIT_MIN_LABELED and hi > lo and os.environ.get("VATLQ_TC_INIT", "1") != "0"
+    done = False
+    if tc_init and lab.numel() > 0:
+        done, _, _ = coreset_init_tc(X, lab, min_d, lo, hi)
     with torch.cuda.device(dev):
-        _lib.check(L.vatlq_coreset_init(_ptr(X), n, d, lo, hi, _ptr(lab) if lab.numel() else None, lab.numel(),
-                                        _ptr(min_d), _ptr(ws), ws_bytes, _stream()), "vatlq_coreset_init")
+        if not done:
+            _lib.check(L.vatlq_coreset_init(_ptr(X), n, d, lo, hi, _ptr(lab) if lab.numel() else None, lab.numel(),
+                                            _ptr(min_d), _ptr(ws), ws_bytes, _stream()), "vatlq_coreset_init")
         _lib.check(L.vatlq_coreset_select(_ptr(X), n, d, lo, hi, _ptr(min_d), _ptr(unc), RULES[rule], float(moks),
                                           float(lam), lab.numel(), int(first_pick), int(k), int(batch), _ptr(out),
                                           C.c_void_p(comm) if comm else None, _ptr(ws), ws_bytes,

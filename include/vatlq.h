@@ -229,6 +229,15 @@ int vatlq_minmax_stats_f64(const double* v, const uint8_t* mask, int64_t n, doub
 int vatlq_fuse_blend(const double* unc, const double* infl, const uint8_t* mask, int64_t n,
                      double combine_weight, double* out, vatlq_stream_t stream);
 
+/* MPE and Margin uncertainties (ActiveLearning.py:762-788): per joint map the <= 5 peaks of
+ * skimage.feature.peak_local_max(map, min_distance=5, num_peaks=5) — 11x11 maximum filter with edge
+ * replication, pixel > map minimum, 5-pixel border excluded, greedy spacing in descending value —
+ * MPE = sum_j entropy(softmax(peaks_j)), Margin = sum_j |peak_0 - peak_1| (fp32).  Either output may be NULL.
+ * ws >= n*J*8 bytes.  (scikit-image is absent from the build container: parity with the library itself is
+ * pinned only against a restatement of its published algorithm, oracle/vatl_oracle.py.) */
+int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, float* mpe, float* margin,
+                   void* ws, size_t ws_bytes, vatlq_stream_t stream);
+
 /* OKS of every item against its ground-truth pose (active_learning/al_metric.py:42-69, call site
  * ActiveLearning.py:309): kpts / gt_kpts [n,17,3] fp32 (x, y, score | visibility), bbox_ann_xyxy [n,4]
  * (converted like alphapose/utils/bbox.py:91-97), oks[n] fp64.  The controller derives moks_queried

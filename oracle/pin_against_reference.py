@@ -219,7 +219,40 @@ def pin_oks(R, O, synth):
     print("OKS pinned:", len(ref), "items, mOKS", moks_ref)
 
 
+def pin_peaks(R, O, synth):
+    """MPE / Margin: the reference's compute_mpe / compute_margin (ActiveLearning.py:762-788) called unbound, with
+    the RESTATED peak_local_max standing in for skimage.feature.peak_local_max (scikit-image is not installed
+    here: the restatement's parity with the library is unpinned; everything around it is the reference's code)."""
+    sys.modules["active_learning.ActiveLearning"].peak_local_max = O.peak_local_max   # (the module, not the class)
+    rng = np.random.default_rng(33)
+    H = synth.heatmaps(6, seed=33)
+    e = np.zeros((2, 17, 64, 48), np.float32)
+    f = e[0]
+    f[0] = 0.25                                                   # constant map: trivial image, no peak
+    f[1, 20, 20] = 1; f[1, 20, 24] = 1; f[1, 20, 25] = 0.9          # equal peaks 4 apart: the second is rejected
+    f[2, 20, 20] = 1; f[2, 20, 25] = 1                              # equal peaks 5 apart: both kept, margin 0
+    f[3, 4, 10] = 2; f[3, 30, 4] = 2; f[3, 59, 10] = 2; f[3, 30, 30] = 0.5   # border peaks are excluded
+    f[4, 10:13, 10:13] = 0.7; f[4, 40, 30] = 0.7                    # plateau: every plateau pixel is a candidate
+    f[5] = rng.normal(0, 0.02, (64, 48)).astype(np.float32)         # pure noise: more than five candidates
+    f[6] = -np.abs(rng.normal(0, 0.02, (64, 48))).astype(np.float32) - 1    # all negative
+    f[7, 5, 5] = 1; f[7, 58, 42] = 0.5                              # first / last interior pixel
+    f[8, 30, 20] = 1                                                # a single peak: entropy(softmax([x])) = 0
+    e[1] = H[0] * 0 + rng.normal(0, 1e-3, (17, 64, 48)).astype(np.float32)
+    H = np.concatenate([H, e], axis=0)
+    fake = SimpleNamespace()
+    mpe = np.array([float(R.AL.compute_mpe(fake, H[i])) for i in range(len(H))])
+    mar = np.array([float(R.AL.compute_margin(fake, H[i])) for i in range(len(H))])
+    same(mpe, [O.mpe_item(H[i]) for i in range(len(H))], "MPE")
+    same(mar, [O.margin_item(H[i]) for i in range(len(H))], "Margin")
+    np.savez_compressed(os.path.join(GOLD, "peaks.npz"), H=H, mpe=mpe, margin=mar)
+    print("MPE / Margin pinned (peak_local_max restated):", mpe[:3], mar[:3])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "peaks":
+        from oracle import vatl_oracle as O
+        pin_peaks(import_reference(), O, importlib.import_module("vatl4pose-wacv2024_b200.synth"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "oks":     # only the OKS fixture (the others are unchanged)
         from oracle import vatl_oracle as O
         pin_oks(import_reference(), O, importlib.import_module("vatl4pose-wacv2024_b200.synth"))
@@ -372,6 +405,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "coreset.npz"), **flat)
     pin_next_rows(R, O, synth)
     pin_oks(R, O, synth)
+    pin_peaks(R, O, synth)
     print("oracle pinned against the reference; fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(f"  {fn}: {os.path.getsize(os.path.join(GOLD, fn)) / 1e6:.2f} MB")

@@ -363,6 +363,9 @@ def pose_unc_pool(H, boxes_xyxy, is_prev, is_next, kind: str) -> np.ndarray:
         if kind == "Entropy":
             out[i] = entropy_item(H[i])
             continue
+        if kind in ("MPE", "Margin"):
+            out[i] = mpe_item(H[i]) if kind == "MPE" else margin_item(H[i])
+            continue
         pose, scores = heatmap_to_coord(H[i], box)
         if kind == "HP":
             out[i] = hp_item(scores)
@@ -418,6 +421,72 @@ def diversity_select(X: np.ndarray, unlabeled_idx, total, k: int):
     div = cosine_rowsum(X[cand])
     d = dict((idx, sc) for idx, sc in zip(cand, div))
     return [int(i) for i, _ in sorted(d.items(), key=lambda x: x[1])][:k]
+
+
+# --------------------------------------------------------------------------------------
+# MPE / Margin (skimage.feature.peak_local_max based)
+# --------------------------------------------------------------------------------------
+
+def peak_local_max(image: np.ndarray, min_distance: int = 1, num_peaks=np.inf) -> np.ndarray:
+    """RESTATEMENT of skimage.feature.peak_local_max (scikit-image 0.24.0, the version the reference pins in
+    requirements.txt:172 / uv.lock; skimage/feature/peak.py) for the arguments the reference passes
+    (ActiveLearning.py:773,784: min_distance=5, num_peaks=5; everything else default: threshold_abs=None,
+    threshold_rel=None, exclude_border=True, p_norm=inf, no labels / footprint).  scikit-image is NOT installed
+    in the build container, so this restatement follows the published algorithm and its parity with the library
+    itself is UNPINNED:
+      footprint = ones((2*min_distance+1,)*2); image_max = ndi.maximum_filter(image, footprint, mode='nearest');
+      mask = image == image_max, all False when every pixel equals its window maximum (trivial image);
+      mask &= image > threshold with threshold = image.min(); the border of width min_distance is excluded;
+      candidates in np.nonzero order are stably sorted by descending intensity; ensure_spacing keeps a peak unless an
+      already kept one lies at Chebyshev distance < min_distance; at most num_peaks are returned, (row, col)."""
+    from scipy import ndimage as ndi
+    size = 2 * min_distance + 1
+    image_max = ndi.maximum_filter(image, footprint=np.ones((size, size), dtype=bool), mode="nearest")
+    out = image == image_max
+    if np.all(out):
+        out[:] = False
+    out &= image > image.min()
+    b = min_distance
+    if b > 0:
+        out[:b, :] = False; out[-b:, :] = False; out[:, :b] = False; out[:, -b:] = False
+    coord = np.nonzero(out)
+    inten = image[coord]
+    order = np.argsort(-inten, kind="stable")
+    coord = np.transpose(coord)[order]
+    kept = []
+    max_out = int(num_peaks) if np.isfinite(num_peaks) else None
+    for c in coord:
+        if all(max(abs(int(c[0]) - int(k[0])), abs(int(c[1]) - int(k[1]))) >= min_distance for k in kept):
+            kept.append(c)
+            if max_out is not None and len(kept) >= max_out:
+                break
+    return np.array(kept, dtype=np.int64).reshape(-1, 2)
+
+
+def mpe_item(hm: np.ndarray, plm=peak_local_max) -> float:
+    """active_learning/ActiveLearning.py:762-778 (compute_mpe): entropy of the softmax of the <= 5 local peak
+    values of every joint map, summed over the joints."""
+    from scipy.special import softmax
+    from scipy.stats import entropy
+    mpe = 0
+    for heatmap in hm:
+        loc = plm(heatmap, min_distance=5, num_peaks=5)
+        peaks = heatmap[loc[:, 0], loc[:, 1]]
+        if peaks.shape[0] > 0:
+            peaks = softmax(peaks)
+            mpe += entropy(peaks)
+    return float(mpe)
+
+
+def margin_item(hm: np.ndarray, plm=peak_local_max) -> float:
+    """active_learning/ActiveLearning.py:780-788 (compute_margin): |top peak - second peak| summed over the joints."""
+    margin = 0
+    for heatmap in hm:
+        loc = plm(heatmap, min_distance=5, num_peaks=5)
+        peaks = heatmap[loc[:, 0], loc[:, 1]]
+        if peaks.shape[0] > 1:
+            margin += np.linalg.norm(peaks[0] - peaks[1])
+    return float(margin)
 
 
 # --------------------------------------------------------------------------------------

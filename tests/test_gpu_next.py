@@ -1,6 +1,7 @@
 """GPU parity of the SURVEY.md §8f rows — HP / TPC / Entropy uncertainties, Influence / Diversity
 scores and the top-k / Diversity selections — against the reference outputs in tests/golden/next.npz
 (written by oracle/pin_against_reference.py) and against the oracle on larger seeded pools."""
+import os
 import warnings
 from types import SimpleNamespace
 
@@ -216,3 +217,17 @@ def test_controller_next_strategies_match_oracle(built_lib, unc, rep, flt):
             assert np.allclose([d[i] for i in range(n)], raw, rtol=RTOL)
         labeled = labeled + got
         assert al.outcome() is None
+
+
+@pytest.mark.parametrize("kind", ["MPE", "Margin"])
+def test_peak_uncertainties_match_oracle(built_lib, kind):
+    """MPE / Margin (ActiveLearning.py:762-788) against the oracle, whose compute_mpe / compute_margin were run
+    through the REFERENCE's own methods with the restated peak_local_max (golden), plus edge maps: plateaus,
+    constant maps (trivial image -> no peak), peaks on the excluded border, ties."""
+    v = built_lib
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "peaks.npz"))
+    H = z["H"]
+    got_mpe, got_mar = v.ops.peak_uncertainty(torch.from_numpy(H).cuda())
+    got = (got_mpe if kind == "MPE" else got_mar).cpu().numpy()
+    ref = z["mpe" if kind == "MPE" else "margin"]
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), np.abs(got - ref).max()

@@ -99,7 +99,7 @@ def test_strategy_names_and_errors():
         with pytest.raises(ValueError):
             ActiveLearning(*_cfg_opt(*bad), eval_len=10)
     # names that exist in the reference but are not accelerated dispatch back to the reference
-    for u in ("MPE", "Margin", "VL4Pose"):
+    for u in ("VL4Pose",):
         al = ActiveLearning(*_cfg_opt(u), eval_len=10)
         with pytest.raises(NotImplementedError):
             al._require_accelerated()
@@ -107,7 +107,7 @@ def test_strategy_names_and_errors():
         al = ActiveLearning(*_cfg_opt("THC", "None", f), eval_len=10)
         with pytest.raises(NotImplementedError):
             al._require_accelerated()
-    for u in ("THC", "THC_L1", "WPU", "WPU_hybrid", "THC+WPU", "None", "HP", "TPC", "Entropy"):
+    for u in ("THC", "THC_L1", "WPU", "WPU_hybrid", "THC+WPU", "None", "HP", "TPC", "Entropy", "MPE", "Margin"):
         ActiveLearning(*_cfg_opt(u), eval_len=10)._require_accelerated()
     for r, f in (("Influence", "None"), ("Random", "Diversity"), ("None", "Random"), ("Influence", "Coreset")):
         ActiveLearning(*_cfg_opt("THC", r, f), eval_len=10)._require_accelerated()

@@ -203,7 +203,7 @@ def coreset_selection(self, embeddings, uncertainty):
 
 _REFERENCE_ONLY_UNC = ("VL4Pose",)                      # the reference's own VL4Pose branch is an unfinished stub (:390-391)
 _PEAK_UNC = ("MPE", "Margin")                           # skimage.peak_local_max based (:762-788)
-_SINGLE_UNC = ("HP", "TPC", "Entropy")
+_SINGLE_UNC = ("HP", "TPC", "Entropy", "MPE", "Margin")
 
 
 class ActiveLearning:
@@ -306,7 +306,7 @@ class ActiveLearning:
     # -- dispatch guard: names this package does not accelerate stay on the reference ----
     def _require_accelerated(self):
         u = self.uncertainty
-        if u in _REFERENCE_ONLY_UNC or (u in _PEAK_UNC and not hasattr(ops, "peak_uncertainty")):
+        if u in _REFERENCE_ONLY_UNC:
             raise NotImplementedError(
                 f"uncertainty '{u}' is not on the accelerated path: run the reference's "
                 "ActiveLearning.eval_and_query (active_learning/ActiveLearning.py:329-401) for it")

@@ -67,9 +67,164 @@ __global__ void __launch_bounds__(128) oks_kernel(const float* __restrict__ kpts
   oks[i] = __ddiv_rn(np_sum_f64(e, m), (double)m);
 }
 
+// ------------------------------------------------------------------------------------
+// MPE and Margin (ActiveLearning.py:762-788): both need skimage.feature.peak_local_max(heatmap,
+// min_distance=5, num_peaks=5) of every joint map.  One warp per map, staged in shared memory:
+//   11 x 11 maximum filter with edge replication ('nearest'), separable (rows, then columns);
+//   mask = (pixel == window max) & (pixel > map minimum), empty when EVERY pixel equals its window
+//   maximum, border of 5 pixels excluded;
+//   up to five rounds of "best remaining mask pixel" (largest value, lowest row-major index on ties —
+//   np.argsort(-v, kind='stable') over np.nonzero order), each accepted peak clearing the mask within
+//   Chebyshev distance < 5 (ensure_spacing, p_norm = inf).
+//   MPE    += entropy(softmax(peaks))   (fp32, scipy.special.softmax / scipy.stats.entropy)
+//   Margin += |peaks[0] - peaks[1]|     when at least two peaks exist
+// ------------------------------------------------------------------------------------
+constexpr int kPeakWarps = 4;
+constexpr int kPeakMinDist = 5;
+
+__global__ void __launch_bounds__(kPeakWarps * 32)
+peak_unc_kernel(const float* __restrict__ H, long long maps, int h, int w, float* __restrict__ mpe_map,
+                float* __restrict__ margin_map) {
+  extern __shared__ float s_peak[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long mi = (long long)blockIdx.x * kPeakWarps + wp;
+  if (mi >= maps) return;
+  const int npx = h * w;
+  float* img = s_peak + (size_t)wp * 2 * npx;      // the map
+  float* aux = img + npx;                         // row maxima, then the peak mask (as 0 / 1)
+  const float* src = H + (size_t)mi * npx;
+  float vmin = INFINITY;
+  for (int i = lane; i < npx; i += 32) {
+    const float v = __ldg(src + i);
+    img[i] = v;
+    vmin = fminf(vmin, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+  __syncwarp();
+  for (int i = lane; i < npx; i += 32) {           // row pass
+    const int y = i / w, x = i - y * w;
+    float m = -INFINITY;
+    for (int dx = -kPeakMinDist; dx <= kPeakMinDist; ++dx) m = fmaxf(m, img[y * w + min(max(x + dx, 0), w - 1)]);
+    aux[i] = m;
+  }
+  __syncwarp();
+  int n_eq = 0;
+  unsigned keep_bits[4] = {0u, 0u, 0u, 0u};        // this lane's mask bits (pixel i = lane + 32 q, q < 128)
+  for (int i = lane, q = 0; i < npx; i += 32, ++q) {   // column pass + mask
+    const int y = i / w, x = i - y * w;
+    float m = -INFINITY;
+    for (int dy = -kPeakMinDist; dy <= kPeakMinDist; ++dy) m = fmaxf(m, aux[min(max(y + dy, 0), h - 1) * w + x]);
+    const float v = img[i];
+    const bool eq = v == m;
+    n_eq += eq ? 1 : 0;
+    const bool interior = y >= kPeakMinDist && y < h - kPeakMinDist && x >= kPeakMinDist && x < w - kPeakMinDist;
+    if (eq && v > vmin && interior) keep_bits[q >> 5] |= 1u << (q & 31);
+  }
+  n_eq = warp_sum(n_eq);
+  __syncwarp();
+  const bool trivial = n_eq == npx;                // every pixel equals its window maximum: no peak at all
+  for (int i = lane, q = 0; i < npx; i += 32, ++q)
+    aux[i] = (!trivial && ((keep_bits[q >> 5] >> (q & 31)) & 1u)) ? 1.f : 0.f;
+  __syncwarp();
+  float peaks[5];
+  int npk = 0;
+  for (int r = 0; r < 5; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < npx; i += 32)
+      if (aux[i] != 0.f) {
+        const float v = img[i];
+        if (v > bv || (v == bv && i < bi)) {
+          bv = v;
+          bi = i;
+        }
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > bv || (v2 == bv && i2 < bi)) {
+        bv = v2;
+        bi = i2;
+      }
+    }
+    if (bi == 0x7fffffff) break;
+    peaks[npk++] = bv;
+    const int py = bi / w, px = bi - py * w;
+    // clear the mask within Chebyshev distance < 5 of the accepted peak (itself included)
+    for (int t = lane; t < (2 * kPeakMinDist - 1) * (2 * kPeakMinDist - 1); t += 32) {
+      const int yy = py + t / (2 * kPeakMinDist - 1) - (kPeakMinDist - 1), xx = px + t % (2 * kPeakMinDist - 1) - (kPeakMinDist - 1);
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) aux[yy * w + xx] = 0.f;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    float mpe = 0.f, margin = 0.f;
+    if (npk > 0) {
+      // scipy.special.softmax (fp32): exp(x - max) / sum; scipy.stats.entropy: pk / sum(pk), sum(entr(pk))
+      float e[5], ssum = 0.f;
+      for (int k = 0; k < npk; ++k) {
+        e[k] = expf(peaks[k] - peaks[0]);          // peaks[0] is the maximum (descending order)
+        ssum = __fadd_rn(ssum, e[k]);
+      }
+      float psum = 0.f;
+      for (int k = 0; k < npk; ++k) {
+        e[k] = __fdiv_rn(e[k], ssum);
+        psum = __fadd_rn(psum, e[k]);
+      }
+      for (int k = 0; k < npk; ++k) {
+        const float pk = __fdiv_rn(e[k], psum);
+        mpe = __fadd_rn(mpe, pk > 0.f ? -pk * logf(pk) : 0.f);
+      }
+    }
+    if (npk > 1) margin = fabsf(peaks[0] - peaks[1]);
+    mpe_map[mi] = mpe;
+    margin_map[mi] = margin;
+  }
+}
+
+// per-frame sums over the joints, in joint order
+__global__ void __launch_bounds__(256) peak_frames_kernel(const float* __restrict__ mpe_map, const float* __restrict__ margin_map,
+                                                          long long n, int J, float* __restrict__ mpe, float* __restrict__ margin) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float a = 0.f, b = 0.f;
+  for (int j = 0; j < J; ++j) {
+    a = __fadd_rn(a, mpe_map[t * J + j]);
+    b = __fadd_rn(b, margin_map[t * J + j]);
+  }
+  if (mpe) mpe[t] = a;
+  if (margin) margin[t] = b;
+}
+
 }  // namespace vatlq
 
 using namespace vatlq;
+
+extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, float* mpe, float* margin, void* ws,
+                              size_t ws_bytes, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_REQUIRE(n >= 0 && J > 0 && h > 2 * kPeakMinDist && w > 2 * kPeakMinDist, "bad shape");
+  if (n == 0) return 0;
+  VQ_REQUIRE(H && ws && (mpe || margin), "null pointer");
+  VQ_REQUIRE(h * w <= 128 * 32 * 4, "map too large (<= 16384 pixels)");
+  const long long maps = (long long)n * J;
+  VQ_REQUIRE(ws_bytes >= (size_t)maps * 8, "workspace must hold 2 floats per map");
+  const size_t smem = (size_t)kPeakWarps * 2 * h * w * sizeof(float);
+  VQ_REQUIRE(smem <= 200 * 1024, "map too large for the shared-memory staging");
+  static size_t configured = 0;
+  if (smem > configured) {
+    VQ_CUDA(cudaFuncSetAttribute(peak_unc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  float* mm = (float*)ws;
+  peak_unc_kernel<<<(unsigned)((maps + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
+  VQ_LAUNCHED();
+  peak_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mm, mm + maps, (long long)n, J, mpe, margin);
+  VQ_LAUNCHED();
+  return 0;
+}
 
 extern "C" int vatlq_oks(const float* kpts, const float* gt_kpts, const float* bbox_ann_xyxy, int64_t n, double* oks,
                          vatlq_stream_t stream_) {

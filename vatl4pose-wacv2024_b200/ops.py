@@ -438,3 +438,18 @@ def oks(kpts: torch.Tensor, gt_kpts: torch.Tensor, bbox_ann_xyxy: torch.Tensor) 
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().vatlq_oks(_ptr(kpts), _ptr(gt), _ptr(bb), n, _ptr(out), _stream()), "vatlq_oks")
     return out
+
+
+def peak_uncertainty(H: torch.Tensor, want_mpe: bool = True, want_margin: bool = True):
+    """MPE / Margin uncertainties (ActiveLearning.py:762-788) of every frame (vatlq_peak_unc): fp32 (n,) each."""
+    H = _cuda(H, torch.float32, "H")
+    if H.dim() != 4:
+        raise _lib.VatlqError("H must be (n,J,h,w)")
+    n, nj, h, w = H.shape
+    mpe = torch.empty(n, dtype=torch.float32, device=H.device) if want_mpe else None
+    mar = torch.empty(n, dtype=torch.float32, device=H.device) if want_margin else None
+    ws = torch.empty(max(n * nj * 2, 1), dtype=torch.float32, device=H.device)
+    with torch.cuda.device(H.device):
+        _lib.check(_lib.lib().vatlq_peak_unc(_ptr(H), n, nj, h, w, _ptr(mpe), _ptr(mar), _ptr(ws), ws.numel() * 4, _stream()),
+                   "vatlq_peak_unc")
+    return mpe, mar

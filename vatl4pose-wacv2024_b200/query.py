@@ -37,7 +37,7 @@ def _require_cuda(dev: torch.device):
         raise _lib.VatlqError("QueryPass needs a CUDA device")
 
 
-SINGLE_UNCERTAINTIES = ("HP", "TPC", "Entropy")   # one fp32 score per item, min-max normalised (:511-516)
+SINGLE_UNCERTAINTIES = ("HP", "TPC", "Entropy", "MPE", "Margin")   # one fp32 score per item, min-max normalised (:511-516)
 
 
 class QueryPass:
@@ -132,6 +132,9 @@ class QueryPass:
         self._carry_pos = pos + m
         if self.single == "Entropy":
             self.aux[sl] = ops.heatmap_entropy(H)
+        elif self.single in ("MPE", "Margin"):
+            mpe, mar = ops.peak_uncertainty(H, want_mpe=self.single == "MPE", want_margin=self.single == "Margin")
+            self.aux[sl] = mpe if self.single == "MPE" else mar
         if self._boxes is not None:
             self._boxes[sl] = boxes_xyxy
         if self._flags is not None:

@@ -238,6 +238,13 @@ int vatlq_fuse_blend(const double* unc, const double* infl, const uint8_t* mask,
 int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, float* mpe, float* margin,
                    void* ws, size_t ws_bytes, vatlq_stream_t stream);
 
+/* Candidate ordering on the device (ActiveLearning.py:527-538, 587-589): out_idx[n] = row ids with mask != 0
+ * (mask NULL: all) by descending (descending != 0) or ascending score, equal scores in ascending id order —
+ * the order Python's stable sorted(..., reverse=True) yields; masked-out rows follow at the end. */
+size_t vatlq_rank_workspace_bytes(int64_t n);
+int vatlq_rank_scores(const double* score, const uint8_t* mask, int64_t n, int descending, int64_t* out_idx,
+                      void* ws, size_t ws_bytes, vatlq_stream_t stream);
+
 /* OKS of every item against its ground-truth pose (active_learning/al_metric.py:42-69, call site
  * ActiveLearning.py:309): kpts / gt_kpts [n,17,3] fp32 (x, y, score | visibility), bbox_ann_xyxy [n,4]
  * (converted like alphapose/utils/bbox.py:91-97), oks[n] fp64.  The controller derives moks_queried

@@ -231,3 +231,22 @@ def test_peak_uncertainties_match_oracle(built_lib, kind):
     got = (got_mpe if kind == "MPE" else got_mar).cpu().numpy()
     ref = z["mpe" if kind == "MPE" else "margin"]
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), np.abs(got - ref).max()
+
+
+def test_rank_scores_equals_python_stable_sort(built_lib):
+    """vatlq_rank_scores reproduces `sorted(dict.items(), key=score, reverse=True)` over a dict in ascending id order
+    (ActiveLearning.py:527-530): ties keep ascending ids; negative values, zeros of both signs, infinities."""
+    v = built_lib
+    rng = np.random.default_rng(3)
+    n = 5000
+    s = np.round(rng.normal(0, 1, n), 1)           # many ties
+    s[:7] = [0.0, -0.0, np.inf, -np.inf, 1e-300, -1e-300, 0.0]
+    mask = (rng.random(n) < 0.7).astype(np.uint8)
+    ids = [i for i in range(n) if mask[i]]
+    for desc in (True, False):
+        expect = [i for i, _ in sorted(((i, s[i]) for i in ids), key=lambda x: x[1], reverse=desc)]
+        got = v.ops.rank_scores(torch.from_numpy(s).cuda(), torch.from_numpy(mask).cuda(), descending=desc).cpu().tolist()
+        assert got == expect
+        assert v.ops.rank_scores(torch.from_numpy(s).cuda(), torch.from_numpy(mask).cuda(), descending=desc, count=17).cpu().tolist() == expect[:17]
+    allrows = v.ops.rank_scores(torch.from_numpy(s).cuda()).cpu().tolist()
+    assert allrows == [i for i, _ in sorted(enumerate(s), key=lambda x: x[1], reverse=True)]

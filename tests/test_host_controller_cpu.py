@@ -134,12 +134,18 @@ def _install_stand_ins(monkeypatch, v):
                              gt[i].reshape(-1).double().numpy()) for i in range(n)]
         return torch.tensor(out, dtype=torch.float64)
 
+    def rank_scores(score, mask=None, descending=True, count=None):
+        sc = score.numpy()
+        idx = [i for i in range(len(sc)) if mask is None or bool(mask[i])]
+        order = sorted(idx, key=lambda t: sc[t], reverse=descending)       # the reference's stable sorted() (:529,587)
+        return torch.tensor(order if count is None else order[:count], dtype=torch.int64)
+
     def pack_ae_weights(weights, device):
         return [O.make_autoencoder(weights)], 42, 4
 
     for name, fn in dict(_flags=_flags, heatmap_scan=heatmap_scan, heatmap_entropy=heatmap_entropy,
                          pose_uncertainty=pose_uncertainty, cosine_rowsum=cosine_rowsum, minmax_f64=minmax_f64,
-                         blend_scores=blend_scores, fuse_scores=fuse_scores, coreset_select=coreset_select, wpu=wpu, oks=oks,
+                         blend_scores=blend_scores, fuse_scores=fuse_scores, coreset_select=coreset_select, wpu=wpu, oks=oks, rank_scores=rank_scores,
                          pack_ae_weights=pack_ae_weights).items():
         monkeypatch.setattr(ops, name, fn)
 

@@ -429,20 +429,22 @@ class ActiveLearning:
             self.combine_weight.append(qp.combine_weight)                             # (:486-488)
         if self.uncertainty != "None" and len(unl_idx) not in (0, 1):
             self.uncertainty_dict["Round" + str(self.round_cnt)] = UNC                # (:510,514)
-        s = order = None
+        order = None
         if len(unl_idx) in (0, 1) or self.filter in ("None", "Diversity", "Random"):
-            # unlabelled ids by descending score, ties in id order (sorted() is stable) (:527-530)
-            s = score.cpu().numpy()[unl_idx] if unl_idx else np.zeros(0)
-            order = sorted(range(len(unl_idx)), key=lambda t: s[t], reverse=True)
+            # unlabelled ids by descending score, ties in id order (sorted() is stable) (:527-530): ranked on the
+            # device, only the ids that are used come back
+            want = self.query_size if (len(unl_idx) in (0, 1) or self.filter == "None") else 8 * self.query_size
+            order = ops.rank_scores(score, unl, descending=True, count=want).cpu().tolist() if unl_idx else []
         if len(unl_idx) in (0, 1) or self.filter == "None":                           # (:533-534,541-542)
-            query_list = sorted(int(unl_idx[t]) for t in order[:self.query_size])
+            query_list = sorted(int(i) for i in order[:self.query_size])
         elif self.filter == "Diversity":                                              # (:537-538,581-590)
-            cand = sorted(int(unl_idx[t]) for t in order[:8 * self.query_size])
-            div = ops.cosine_rowsum(X, rows=torch.as_tensor(cand, dtype=torch.int64, device=dev)).cpu().numpy()
-            by_div = sorted(range(len(cand)), key=lambda t: div[t])
-            query_list = [cand[t] for t in by_div[:self.query_size]]
+            cand = sorted(int(i) for i in order[:8 * self.query_size])
+            cand_t = torch.as_tensor(cand, dtype=torch.int64, device=dev)
+            div = ops.cosine_rowsum(X, rows=cand_t)
+            by_div = ops.rank_scores(div, None, descending=False, count=self.query_size).cpu().tolist()
+            query_list = [cand[t] for t in by_div]
         elif self.filter == "Random":                                                 # (:591-592, random_query :727-734)
-            cand = sorted(int(unl_idx[t]) for t in order[:8 * self.query_size])
+            cand = sorted(int(i) for i in order[:8 * self.query_size])
             query_list = []
             while len(query_list) < self.query_size and len(cand) > 0:
                 q = int(np.random.choice(cand))

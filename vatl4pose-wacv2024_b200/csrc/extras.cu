@@ -2,6 +2,8 @@
 //   * OKS of every item against its ground-truth pose (active_learning/al_metric.py:42-69): the
 //     controller derives moks_queried (the core-set's score weights, ActiveLearning.py:815-821,858)
 //     and the stopping criteria (:707-725) from it.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 
 namespace vatlq {
@@ -198,9 +200,61 @@ __global__ void __launch_bounds__(256) peak_frames_kernel(const float* __restric
   if (margin) margin[t] = b;
 }
 
+// ------------------------------------------------------------------------------------
+// candidate ordering (ActiveLearning.py:527-538, 587-589): ids of the masked-in rows by descending (or ascending)
+// score, ties in ascending id order — what `sorted(dict.items(), key=score, reverse=True)` yields for a dict built in
+// ascending id order (Python's sort is stable; reverse=True keeps equal keys in their original order).
+// Order-preserving 64-bit keys + a stable LSD radix sort (cub::DeviceRadixSort); masked-out rows sort last.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rank_keys_kernel(const double* __restrict__ score, const uint8_t* __restrict__ mask, long long n,
+                                                        int descending, unsigned long long* __restrict__ keys, long long* __restrict__ vals) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = 0xFFFFFFFFFFFFFFFFULL;
+  if (!mask || mask[i]) {
+    double s = score[i];
+    if (s == 0.0) s = 0.0;                                       // -0.0 and +0.0 compare equal in Python
+    unsigned long long b = (unsigned long long)__double_as_longlong(s);
+    b = (b >> 63) ? ~b : (b | 0x8000000000000000ULL);            // ascending order of the doubles
+    k = descending ? ~b : b;
+    if (k == 0xFFFFFFFFFFFFFFFFULL) k -= 1;                      // (keep the sentinel unique to masked-out rows)
+  }
+  keys[i] = k;
+  vals[i] = i;
+}
+
 }  // namespace vatlq
 
 using namespace vatlq;
+
+extern "C" size_t vatlq_rank_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  size_t cb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const long long*)nullptr, (long long*)nullptr, (int)n);
+  return align_up(cb, 256) + 3 * align_up((size_t)n * 8, 256);
+}
+
+extern "C" int vatlq_rank_scores(const double* score, const uint8_t* mask, int64_t n, int descending, int64_t* out_idx,
+                                 void* ws, size_t ws_bytes, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_REQUIRE(n >= 0 && n < (1LL << 31), "n out of range");
+  if (n == 0) return 0;
+  VQ_REQUIRE(score && out_idx && ws, "null pointer");
+  VQ_REQUIRE(ws_bytes >= vatlq_rank_workspace_bytes(n), "workspace too small (vatlq_rank_workspace_bytes)");
+  char* w = (char*)ws;
+  const size_t seg = align_up((size_t)n * 8, 256);
+  unsigned long long* k_in = (unsigned long long*)w;
+  unsigned long long* k_out = (unsigned long long*)(w + seg);
+  long long* v_in = (long long*)(w + 2 * seg);
+  void* tmp = w + 3 * seg;
+  size_t cb = ws_bytes - 3 * seg;
+  rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(score, mask, (long long)n, descending, k_in, v_in);
+  VQ_LAUNCHED();
+  VQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, k_in, k_out, v_in, (long long*)out_idx, (int)n, 0, 64, stream));
+  g_launches.fetch_add(1);
+  return 0;
+}
 
 extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, float* mpe, float* margin, void* ws,
                               size_t ws_bytes, vatlq_stream_t stream_) {

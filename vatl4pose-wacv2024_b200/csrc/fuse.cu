@@ -1,7 +1,7 @@
 // Score fusion of active_learning/ActiveLearning.py:490-516 in float64 on the device:
 // per-criterion min-max over the unlabelled rows, combination, min-max again.  Every
 // operation is a single IEEE double op in the reference's order, so given the same inputs
-// the result is bit-identical to numpy's.
+// the result is bit-identical to numpy's (NaN inputs included: they poison the statistics like np.min / np.max).
 #include "common.cuh"
 
 namespace vatlq {
@@ -46,11 +46,15 @@ __global__ void __launch_bounds__(256) fuse_stats_kernel(const float* __restrict
   double v[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (unl && !unl[i]) continue;
+    // np.min / np.max propagate NaN (fmin drops it): a NaN input sets (min, -max) = (-inf, -inf), which turns
+    // every normalised score into NaN exactly like the reference's (x - min) / (max - min)
     const double t = (double)thc[i];
+    if (t != t) v[0] = v[1] = -INFINITY;
     v[0] = fmin(v[0], t);
     v[1] = fmin(v[1], -t);
     if (wpu) {
       const double w = (double)wpu[i];
+      if (w != w) v[2] = v[3] = -INFINITY;
       v[2] = fmin(v[2], w);
       v[3] = fmin(v[3], -w);
     }
@@ -84,6 +88,7 @@ __global__ void __launch_bounds__(256) fuse_combine_kernel(const float* __restri
       else r = __dadd_rn(__dmul_rn(__dsub_rn(1.0, ratio), a), __dmul_rn(ratio, b));                // :507
     }
     u[i] = r;
+    if (r != r) v[0] = v[1] = -INFINITY;
     v[0] = fmin(v[0], r);
     v[1] = fmin(v[1], -r);
   }

@@ -331,8 +331,10 @@ minmax_stats_f64_kernel(const double* __restrict__ v, const uint8_t* __restrict_
   double lo = INFINITY, nhi = INFINITY;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (mask && !mask[i]) continue;
-    lo = fmin(lo, v[i]);
-    nhi = fmin(nhi, -v[i]);
+    const double x = v[i];
+    if (x != x) lo = nhi = -INFINITY;   // a NaN makes np.min / np.max NaN: (min, -max) = (-inf, -inf) turns every score into NaN
+    lo = fmin(lo, x);
+    nhi = fmin(nhi, -x);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {

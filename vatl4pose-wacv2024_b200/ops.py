@@ -453,3 +453,21 @@ def peak_uncertainty(H: torch.Tensor, want_mpe: bool = True, want_margin: bool =
         _lib.check(_lib.lib().vatlq_peak_unc(_ptr(H), n, nj, h, w, _ptr(mpe), _ptr(mar), _ptr(ws), ws.numel() * 4, _stream()),
                    "vatlq_peak_unc")
     return mpe, mar
+
+
+def rank_scores(score: torch.Tensor, mask=None, descending: bool = True, count: int | None = None) -> torch.Tensor:
+    """Row ids with mask != 0 ordered by score (descending by default), equal scores in ascending id order — the
+    candidate order of ActiveLearning.py:527-530 — computed on the device (vatlq_rank_scores).  Returns the first
+    `count` ids (all masked-in rows when None) as an int64 CUDA tensor."""
+    score = _cuda(score, torch.float64, "score")
+    n = score.numel()
+    mk = _flags(mask, n, score.device, "mask")
+    m = n if mk is None else int(mk.sum().item())
+    out = torch.empty(max(n, 1), dtype=torch.int64, device=score.device)
+    L = _lib.lib()
+    ws_bytes = L.vatlq_rank_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=score.device)
+    with torch.cuda.device(score.device):
+        _lib.check(L.vatlq_rank_scores(_ptr(score), _ptr(mk), n, int(descending), _ptr(out), _ptr(ws), ws_bytes, _stream()),
+                   "vatlq_rank_scores")
+    return out[:m if count is None else min(m, int(count))]

@@ -52,8 +52,10 @@ class QueryPass:
         self.uncertainty = uncertainty
         # dispatch order of ActiveLearning.py:329-401: exact names first, then the substring tests
         self.single = uncertainty if uncertainty in SINGLE_UNCERTAINTIES else None
+        # elif order of the reference: a name containing "THC" is THC (even "THC_WPU..."); only the exact string
+        # "THC+WPU" enables the two-criterion path (:345,364,403,494)
         self.use_thc = self.single is None and "THC" in uncertainty
-        self.use_wpu = self.single is None and "WPU" in uncertainty
+        self.use_wpu = self.single is None and (uncertainty == "THC+WPU" or ("WPU" in uncertainty and "THC" not in uncertainty))
         if not (self.use_thc or self.use_wpu or self.single or uncertainty == "None"):
             raise ValueError("Uncertainty type is not supported by the accelerated path")
         self.nj, self.hm = n_joints, tuple(hm_shape)

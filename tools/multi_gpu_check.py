@@ -23,7 +23,7 @@ def main():
     if rank == 0:
         print("candidate exchange:", "peer-memory mailbox" if comm.p2p else "ncclAllGather", flush=True)
     ok = True
-    for n, k, d, n_lab, moks in ((1501, 97, 2048, 0, 0.0), (4003, 160, 2048, 300, 0.6), (777, 40, 256, 50, 0.6)):
+    for n, k, d, n_lab, moks in ((1501, 97, 2048, 0, 0.0), (4003, 160, 2048, 300, 0.6), (777, 40, 256, 50, 0.6), (9001, 200, 2048, 900, 0.6)):
         rng = np.random.default_rng(n)
         ids, ip, inx = synth.track_flags(n, rng, mean_len=12.0)
         H = synth.heatmaps(n, seed=n, track_ids=ids)
@@ -53,6 +53,39 @@ def main():
         if rank == 0:
             print(f"n={n} k={k} d={d} labelled={n_lab}: picks_equal={same} thc_equal={thc_same} wpu_equal={wpu_same} "
                   f"all_ranks_ok={bool(flag.item())} stats={res.stats}", flush=True)
+        ok = ok and bool(flag.item())
+    # ---- the other strategies: sharded run vs the same code on ONE rank holding the whole pool
+    solo = None
+    for r in range(world):                      # (every rank must take part in every new_group call)
+        g = td.new_group([r])
+        if r == rank:
+            solo = g
+    n, k = 2203, 60
+    rng = np.random.default_rng(77)
+    ids, ip, inx = synth.track_flags(n, rng, mean_len=9.0)
+    H = synth.heatmaps(n, seed=77, track_ids=ids)
+    Hpos = np.abs(H) + np.float32(1e-3)         # (Entropy is -inf on maps with negatives: use a positive pool for it)
+    boxes = synth.boxes_xyxy(n, seed=77)
+    X = synth.embeddings(n, d=2048, seed=78)
+    labeled = sorted(np.random.default_rng(6).choice(n, 200, replace=False).tolist())
+    lo, hi = vd.shard_range(n, rank, world)
+    to = lambda a, sl=slice(None): torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev)
+    for unc, rep, flt in (("TPC", "Influence", "None"), ("Entropy", "None", "Diversity"), ("MPE", "None", "None"),
+                          ("Margin", "Influence", "Diversity"), ("HP", "Influence", "Coreset"), ("None", "Influence", "Coreset")):
+        Hs = Hpos if unc == "Entropy" else H
+        rule = "dist" if unc == "None" else "w_unc"
+        kw = dict(uncertainty=unc, representativeness=rep, filter=flt, rule=rule, first_pick=-1)
+        multi = vd.distributed_query(to(Hs, slice(lo, hi)), to(boxes, slice(lo, hi)), to(ip.astype(np.uint8), slice(lo, hi)),
+                                     to(inx.astype(np.uint8), slice(lo, hi)), to(X, slice(lo, hi)), None, labeled, n, k, 0.6, 0.01,
+                                     comm=comm, **kw)
+        one = vd.distributed_query(to(Hs), to(boxes), to(ip.astype(np.uint8)), to(inx.astype(np.uint8)), to(X), None, labeled,
+                                   n, k, 0.6, 0.01, comm=None, group=solo, **kw)
+        same = multi.picks.cpu().tolist() == one.picks.cpu().tolist()
+        close = bool(torch.allclose(multi.unc, one.unc, rtol=1e-9, atol=1e-12, equal_nan=True))
+        flag = torch.tensor([int(same and close)], device=dev)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        if rank == 0:
+            print(f"{unc}+{rep}_{flt}filter: picks_equal={same} scores_close={close} all_ranks_ok={bool(flag.item())}", flush=True)
         ok = ok and bool(flag.item())
     comm.close()
     td.barrier()

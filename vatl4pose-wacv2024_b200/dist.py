@@ -128,9 +128,14 @@ class Comm:
 def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_local, ae_weights, labeled_global,
                       n: int, k: int, moks: float = 0.0, lam: float = 0.01, uncertainty: str = "THC+WPU",
                       thc_vs_wpu: str = "const", rule: str = "w_unc", batch: int = 16, comm: Comm | None = None,
-                      group=None, first_pick: int = -1):
+                      group=None, first_pick: int = -1, representativeness: str = "None", filter: str = "Coreset"):
     """One query over a pool sharded across the ranks of `group` (one process per GPU).
-    Every rank passes its slice of the pool and gets the same global pick list back."""
+    Every rank passes its slice of the pool and gets the same global pick list back.
+    uncertainty: any accelerated name (THC*, WPU*, THC+WPU, HP, TPC, Entropy, MPE, Margin, None);
+    representativeness: "None" or "Influence" (ActiveLearning.py:467-477); filter: "Coreset" (:609-614),
+    "None" (top-k, :533-534) or "Diversity" (:581-590).  Scoring is sharded (halo frame / halo coordinates for
+    THC / TPC, MIN all-reduces for the normalisations, a SUM all-reduce of the cosine column sums for
+    Influence); the fused scores are all-gathered (8 B per item) and the final ordering runs replicated."""
     from . import ops
     from .query import QueryPass, QueryResult
     rank, world = td.get_rank(group), td.get_world_size(group)
@@ -152,12 +157,35 @@ def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_loca
         unl[torch.from_numpy(mine).to(dev)] = 0
     # (group=None means the default group to torch.distributed but "single GPU" to QueryPass.fuse)
     fuse_group = (group if group is not None else td.group.WORLD) if world > 1 else None
-    unc_local = qp.fuse(unl, thc_vs_wpu, labeled_ratio=lab.size / max(n, 1), group=fuse_group,
-                        n_unlabeled_global=n - lab.size)
-    X = allgather_rows(X_local, n, world, group)
-    unc = allgather_rows(unc_local, n, world, group)
-    picks, st = ops.coreset_select(X, unc, lab, k, moks, lam, rule=rule, batch=batch, first_pick=first_pick,
-                                   comm=comm.handle if comm is not None else None,
-                                   row_range=(lo, hi) if world > 1 else None)
-    return QueryResult(picks=picks, thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts, unc=unc,
+    n_unl = n - lab.size
+    score_local = qp.fuse(unl, thc_vs_wpu, labeled_ratio=lab.size / max(n, 1), group=fuse_group, n_unlabeled_global=n_unl)
+    if representativeness == "Influence" and n_unl > 1:                      # (:467-477, 517-526)
+        rows = torch.nonzero(unl, as_tuple=False).flatten()
+        infl = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+        infl[rows] = ops.cosine_rowsum(X_local, rows=rows, group=fuse_group)
+        infl = ops.minmax_f64(infl, unl, group=fuse_group)
+        score_local = ops.blend_scores(score_local, infl, qp.combine_weight, unl) if uncertainty != "None" else infl
+    elif representativeness not in ("None", "Influence"):
+        raise ValueError("Representativeness type is not supported by distributed_query")
+    score = allgather_rows(score_local, n, world, group)
+    if filter == "Coreset":
+        X = allgather_rows(X_local, n, world, group)
+        picks, st = ops.coreset_select(X, score, lab, k, moks, lam, rule=rule, batch=batch, first_pick=first_pick,
+                                       comm=comm.handle if comm is not None else None,
+                                       row_range=(lo, hi) if world > 1 else None)
+    elif filter in ("None", "Diversity"):
+        unl_g = torch.ones(n, dtype=torch.uint8, device=dev)
+        if lab.size:
+            unl_g[torch.from_numpy(lab).to(dev)] = 0
+        st = None
+        if filter == "None" or n_unl <= 1:                                   # (:533-534, 541-542)
+            picks = torch.sort(ops.rank_scores(score, unl_g, descending=True, count=k)).values
+        else:                                                                # (:537-538, 581-590)
+            X = allgather_rows(X_local, n, world, group)
+            cand = torch.sort(ops.rank_scores(score, unl_g, descending=True, count=8 * k)).values
+            div = ops.cosine_rowsum(X, rows=cand)
+            picks = cand[ops.rank_scores(div, None, descending=False, count=k)]
+    else:
+        raise ValueError("Filter type is not supported by distributed_query")
+    return QueryResult(picks=picks, thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts, unc=score,
                        combine_weight=qp.combine_weight, stats=st)

@@ -12,7 +12,9 @@ def _select(v, X, unc, lab, k, moks, batch, mode, min_rows=0):
     v.ops.set_prune(mode, min_rows)
     v.ops.prune_stats(reset=True)
     try:
-        picks, st, md, _ = v.ops.coreset_select(X, unc, lab, k, moks, 0.01, batch=batch, return_state=True)
+        # (tc_init=False: these tests are about the exact passes, including the labelled-set initialisation passes;
+        #  the tensor-core initialisation has its own tests in test_gpu_tc.py)
+        picks, st, md, _ = v.ops.coreset_select(X, unc, lab, k, moks, 0.01, batch=batch, return_state=True, tc_init=False)
         torch.cuda.synchronize()
     finally:
         v.ops.set_prune("env", -1)

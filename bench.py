@@ -345,8 +345,11 @@ def cpu_baseline_entry(a, n, k, moks):
         return {"value": None, "error": repr(exc)[:300]}
 
 
-def pass_roofline(lib, nl, streamed_frac, steps, ms_step, prune, no_prune):
-    """roofline of the dominant kernel (the core-set pass over X) from the library's per-launch CUDA-event timing"""
+def pass_roofline(lib, nl, streamed_frac, steps, ms_step, prune, no_prune, dmma_peak_fma):
+    """roofline of the dominant kernel (the core-set pass over X) from the library's per-launch CUDA-event timing.
+    A pass streams `streamed_frac` of the owned rows once and multiplies every streamed 8-row tile with the launch's
+    centres on the fp64 tensor cores (DMMA): both the HBM and the fp64-tensor fraction are reported, `bound` names the
+    resource that is closer to its measured peak."""
     import ctypes as C
     tot_ms, n_pass, n_picks = C.c_double(), C.c_int64(), C.c_int64()
     lib.vatlq_profile_read(C.byref(tot_ms), C.byref(n_pass), C.byref(n_picks), 1)
@@ -359,19 +362,29 @@ def pass_roofline(lib, nl, streamed_frac, steps, ms_step, prune, no_prune):
     per_pass_bytes = nl * D * 4 * streamed_frac + 40 * nl
     picks_per_launch = n_picks.value / n_pass.value
     avg_s = tot_ms.value / n_pass.value * 1e-3
-    achieved = per_pass_bytes / avg_s / 1e9
-    return {"kernel": "pass_kernel_tma (core-set distance update: TMA-staged tiles, fp64 tensor-core DMMA, row finishing)",
-            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+    gbs = per_pass_bytes / avg_s / 1e9
+    fma = nl * streamed_frac * D * picks_per_launch / avg_s          # algorithmic fp64 FMAs (padding centres not counted)
+    hbm = {"achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs, "peak_source": peak_src}
+    tens = {"achieved": 2 * fma / 1e12, "peak": 2 * dmma_peak_fma / 1e12, "unit": "TFLOP/s (fp64, mma.sync.m8n8k4 DMMA)",
+            "frac": fma / dmma_peak_fma if dmma_peak_fma else None,
+            "peak_source": "measured live by vatlq_measure_fp64_mma (saturating DMMA kernel; MEASURED_PEAKS.json has no fp64 figure)"}
+    use_t = tens["frac"] is not None and tens["frac"] > hbm["frac"]
+    top = tens if use_t else hbm
+    return {"kernel": "pass_kernel_tma (core-set distance update: TMA-staged tiles, fp64 tensor-core DMMA, row finishing; "
+                      "paired form: 16 centres per read of X by a cluster of two CTAs)",
+            "bound": "tensor" if use_t else "hbm", "achieved": top["achieved"], "peak": top["peak"],
+            "unit": "TFLOP/s" if use_t else "GB/s", "frac": top["frac"],
             "traffic": ncu_traffic("pass_kernel" if no_prune else "pass_kernel_pruned", nl),
-            "peak_source": peak_src, "avg_launch_us": avg_s * 1e6, "launches_timed": n_pass.value,
+            "peak_source": top["peak_source"], "hbm": hbm, "fp64_tensor": tens,
+            "avg_launch_us": avg_s * 1e6, "launches_timed": n_pass.value,
             "algorithmic_bytes_per_launch": per_pass_bytes, "streamed_fraction_of_X": streamed_frac,
             "unpruned_bytes_per_launch": nl * D * 4 + 40 * nl, "segments": prune["segments"],
             "greedy_steps_per_launch": picks_per_launch, "algorithmic_bytes_per_greedy_step": per_step_bytes,
             "greedy_equivalent_gbs": picks_per_launch * per_step_bytes / avg_s / 1e9,
-            "fp64_fma_per_s": picks_per_launch * nl * D / avg_s,
             "share_of_step": tot_ms.value / steps / ms_step,
-            "note": "frac charges a pass the bytes it moves ONCE although it applies greedy_steps_per_launch "
-                    "greedy steps (exact batching); greedy_equivalent_gbs is SURVEY 8d's per-step bytes x steps / time"}
+            "note": "a launch applies greedy_steps_per_launch greedy steps for ONE read of the rows it streams (exact batching; "
+                    "the exact triangle filter skips the other rows): hbm charges those bytes once, fp64_tensor counts the "
+                    "8-row x centre x 2048 FMAs of the streamed tiles; greedy_equivalent_gbs is SURVEY 8d's per-step bytes x steps / time"}
 
 
 def run_controls(a, n, dev):
@@ -473,7 +486,8 @@ def full_query(a, n, n_lab, k, moks, config, rank, world, local, dev):
     launches = vatlq._lib.launch_count() - launches0
     prune = ops.prune_stats(reset=True)
     streamed_frac = prune["streamed"] / prune["tiles"] if prune["tiles"] else 1.0
-    roof = pass_roofline(lib, nl, streamed_frac, a.steps, ms_step, prune, a.no_prune)
+    dmma_peak = ops.measure_fp64_mma(dev)
+    roof = pass_roofline(lib, nl, streamed_frac, a.steps, ms_step, prune, a.no_prune, dmma_peak)
     lib.vatlq_profile_passes(0)
     st = res.stats
     picks_ref = res.picks.clone()
@@ -507,7 +521,10 @@ def full_query(a, n, n_lab, k, moks, config, rank, world, local, dev):
             if n2.value > 0 and t2.value > 0:
                 full = nl * D * 4 + 40 * nl
                 s2 = t2.value / n2.value * 1e-3
-                unpruned = {"achieved": full / s2 / 1e9, "frac": full / s2 / 1e9 / peak_gbs, "avg_launch_us": s2 * 1e6,
+                fma2 = nl * D * (p2.value / n2.value) / s2
+                unpruned = {"hbm_gbs": full / s2 / 1e9, "hbm_frac": full / s2 / 1e9 / peak_gbs,
+                            "fp64_tensor_tflops": 2 * fma2 / 1e12, "fp64_tensor_frac": fma2 / dmma_peak if dmma_peak else None,
+                            "avg_launch_us": s2 * 1e6,
                             "launches_timed": n2.value, "algorithmic_bytes_per_launch": full,
                             "traffic": ncu_traffic("pass_kernel", nl), "query_ms": e0.elapsed_time(e1),
                             "picks_equal_pruned_run": bool(torch.equal(r2.picks, picks_ref))}
@@ -593,23 +610,47 @@ def run_e2e(a, segs, ip, inx, bb, Xl, W, labeled, n, nl, k, moks, world, comm, d
     from vatlq import dist as vd, ops
     from vatlq.query import QueryPass
     chunk = 4096
+    frame_elems = 17 * 64 * 48
+    # host budget: all ranks of the box together pin at most ~40 % of the available host memory
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail = 64 << 30
+    budget_frames = max(chunk, int(0.4 * avail / max(1, world) / FRAME_BYTES) // chunk * chunk)
     # pinned host copies of the distinct heat-map buffers (segments that view one ring share one host copy)
-    host = {}
+    uniq = {}
     for _, seg in segs:
-        base = seg.untyped_storage().data_ptr()
-        if base not in host:
+        uniq.setdefault(seg.untyped_storage().data_ptr(), seg)
+    need_frames = sum(torch.empty(0, dtype=sg.dtype, device=dev).set_(sg.untyped_storage()).numel() // frame_elems for sg in uniq.values())
+    exact = need_frames <= budget_frames
+    hsegs = []
+    if exact:
+        host = {}
+        for base, seg in uniq.items():
             full = torch.empty(0, dtype=seg.dtype, device=dev).set_(seg.untyped_storage())
             hb = torch.empty(full.shape, dtype=seg.dtype, pin_memory=True)
-            step = chunk * 17 * 64 * 48
+            step = chunk * frame_elems
             for s in range(0, full.numel(), step):
                 hb[s:s + step].copy_(full[s:s + step])
             host[base] = hb
-    torch.cuda.synchronize()
-    hsegs = []
-    for pos, seg in segs:
-        hb = host[seg.untyped_storage().data_ptr()]
-        off = seg.storage_offset()
-        hsegs.append((pos, hb[off:off + seg.numel()].view(seg.shape)))
+        torch.cuda.synchronize()
+        for pos, seg in segs:
+            hb = host[seg.untyped_storage().data_ptr()]
+            off = seg.storage_offset()
+            hsegs.append((pos, hb[off:off + seg.numel()].view(seg.shape)))
+    else:
+        # the rank's distinct frames do not fit the host budget: a pinned ring of budget_frames frames is cycled
+        # (same bytes per step over PCIe; the scores then differ from the resident run, so the pick check is skipped)
+        first = segs[0][1]
+        R = min(budget_frames, first.shape[0] // chunk * chunk) or min(budget_frames, first.shape[0])
+        ring = torch.empty((R,) + tuple(first.shape[1:]), dtype=first.dtype, pin_memory=True)
+        for s in range(0, R, chunk):
+            ring[s:s + chunk].copy_(first[s:s + chunk])
+        torch.cuda.synchronize()
+        for pos, seg in segs:
+            m = seg.shape[0]
+            for s in range(0, m, R):
+                hsegs.append((pos + s, ring[:min(R, m - s)]))
     Xh = torch.empty(Xl.shape, dtype=Xl.dtype, pin_memory=True); Xh.copy_(Xl)
     bbh, iph, inxh = bb.cpu().pin_memory(), ip.cpu().pin_memory(), inx.cpu().pin_memory()
     torch.cuda.synchronize()
@@ -679,7 +720,7 @@ def run_e2e(a, segs, ip, inx, bb, Xl, W, labeled, n, nl, k, moks, world, comm, d
             torch.cuda.synchronize()
 
     p = step()
-    same = bool(torch.equal(p, picks_ref.cpu()))
+    same = bool(torch.equal(p, picks_ref.cpu())) if exact else None
     reps = max(1, min(a.steps, 3))
     sync()
     t0 = time.perf_counter()
@@ -693,7 +734,7 @@ def run_e2e(a, segs, ip, inx, bb, Xl, W, labeled, n, nl, k, moks, world, comm, d
     return {"value": n / float(dt.item()), "unit": UNIT, "ms_per_step": float(dt.item()) * 1e3,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * 8), "steps": reps,
             "h2d_gbs": h2d / float(dt.item()) / 1e9,
-            "picks_equal_resident_run": same,
+            "picks_equal_resident_run": same, "host_frames_exact": exact,
             "api": "vatlq.QueryPass.score_chunk + fuse + ops.coreset_select (host pinned inputs streamed through "
                    "3 staging buffers, per rank)"}
 
@@ -784,7 +825,7 @@ def small_config(a, n, k, moks, config, rank, world, dev):
     if a.config == 3:
         prune = ops.prune_stats(reset=True)
         sf = prune["streamed"] / prune["tiles"] if prune["tiles"] else 1.0
-        roof = pass_roofline(lib, n, sf, a.steps, ms_step, prune, a.no_prune)
+        roof = pass_roofline(lib, n, sf, a.steps, ms_step, prune, a.no_prune, ops.measure_fp64_mma(dev))
         lib.vatlq_profile_passes(0)
         picks_host = state["picks"].cpu().numpy()
         digest = sha_picks(picks_host)

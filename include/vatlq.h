@@ -252,6 +252,11 @@ int vatlq_rank_scores(const double* score, const uint8_t* mask, int64_t n, int d
 int vatlq_oks(const float* kpts, const float* gt_kpts, const float* bbox_ann_xyxy, int64_t n, double* oks,
               vatlq_stream_t stream);
 
+/* fp64 tensor-core (mma.sync.m8n8k4.f64, DMMA) peak of the current device in FMA/s, measured with a saturating
+ * register-only kernel (about 10 ms): the roofline denominator of the paired core-set pass, which is bound by the
+ * DMMA pipe rather than by HBM.  ws >= 4 * SMs * 256 * 8 bytes. */
+int vatlq_measure_fp64_mma(double* host_fma_per_s, void* ws, size_t ws_bytes, vatlq_stream_t stream);
+
 /* Timing of the dominant kernel (the pass over X) for bench.py's roofline: when enabled,
  * vatlq_coreset_select brackets every pass launch with CUDA events on `stream`; read returns
  * the summed duration of the passes that applied picks, their number and the picks applied.

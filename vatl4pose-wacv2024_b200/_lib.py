@@ -43,6 +43,7 @@ SIGNATURES = {
     "vatlq_peak_unc": (_int, [_vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "vatlq_rank_workspace_bytes": (_sz, [_i64]),
     "vatlq_rank_scores": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "vatlq_measure_fp64_mma": (_int, [_vp, _vp, _sz, _vp]),
     "vatlq_oks": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "vatlq_profile_passes": (_int, [_int]),
     "vatlq_profile_read": (_int, [_vp, _vp, _vp, _int]),

@@ -4,6 +4,8 @@
 //     and the stopping criteria (:707-725) from it.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vatlq {
@@ -223,9 +225,60 @@ __global__ void __launch_bounds__(256) rank_keys_kernel(const double* __restrict
   vals[i] = i;
 }
 
+// ------------------------------------------------------------------------------------
+// fp64 tensor-core peak, measured on the device the library runs on: the roofline denominator of the core-set
+// pass once it is bound by the DMMA pipe (MEASURED_PEAKS.json only carries the HBM and bf16 figures).
+// 8 independent accumulator chains per warp, 8 warps per CTA, 4 CTAs per SM: the pipe is saturated.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    c[k][0] = threadIdx.x * 1e-9;
+    c[k][1] = k;
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace vatlq
 
 using namespace vatlq;
+
+extern "C" int vatlq_measure_fp64_mma(double* host_fma_per_s, void* ws, size_t ws_bytes, vatlq_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int grid = sm_count() * 4, iters = 4096;
+  VQ_REQUIRE(host_fma_per_s && ws && ws_bytes >= (size_t)grid * 256 * 8, "workspace must hold 4*SMs*256 doubles");
+  cudaEvent_t e0, e1;
+  VQ_CUDA(cudaEventCreate(&e0));
+  VQ_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {          // first repetition warms up; best of the rest
+    cudaEventRecord(e0, stream);
+    dmma_peak_kernel<<<grid, 256, 0, stream>>>((double*)ws, iters, 1.0000001, 0.9999999);
+    cudaEventRecord(e1, stream);
+    VQ_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    // one m8n8k4 DMMA = 8*8*4 = 256 FMA per warp
+    const double fma = (double)grid * 8.0 * iters * 8.0 * 256.0;
+    if (rep > 0 && ms > 0.f) best = std::max(best, fma / (ms * 1e-3));
+  }
+  g_launches.fetch_add(4);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *host_fma_per_s = best;
+  return 0;
+}
 
 extern "C" size_t vatlq_rank_workspace_bytes(int64_t n) {
   if (n <= 0) return 0;

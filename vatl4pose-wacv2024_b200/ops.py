@@ -471,3 +471,13 @@ def rank_scores(score: torch.Tensor, mask=None, descending: bool = True, count: 
         _lib.check(L.vatlq_rank_scores(_ptr(score), _ptr(mk), n, int(descending), _ptr(out), _ptr(ws), ws_bytes, _stream()),
                    "vatlq_rank_scores")
     return out[:m if count is None else min(m, int(count))]
+
+
+def measure_fp64_mma(device=None) -> float:
+    """fp64 tensor-core (DMMA) peak of the device in FMA/s, measured live (vatlq_measure_fp64_mma)."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ws = torch.empty(4 * 256 * 8 * 1024, dtype=torch.uint8, device=dev)
+    out = C.c_double()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vatlq_measure_fp64_mma(C.byref(out), _ptr(ws), ws.numel(), _stream()), "vatlq_measure_fp64_mma")
+    return float(out.value)

@@ -23,10 +23,16 @@ for _ in range(2):
     r = ops.heatmap_scan(H, ip, inx, bb)
 ops.heatmap_entropy(H)
 torch.cuda.synchronize()
+mp = ops.peak_uncertainty(H[:4000])
+torch.cuda.synchronize()
 del H
-X = synth.device_embeddings(rows, dev, seed=2)
+X = synth.pool_embeddings(rows, device=dev)
 ops.cosine_rowsum(X)
-unc = torch.rand(rows, dtype=torch.float64, device=dev)
+unc = synth.pool_unc(rows, device=dev)
 picks, st = ops.coreset_select(X, unc, [], k, 0.0, 0.01, batch=batch)
 torch.cuda.synchronize()
 print("ok", st, ops.prune_stats())
+if os.environ.get("PROF_TC", "1") != "0":      # the tensor-core labelled-set initialisation (tc_prefilter / tc_rescore)
+    lab = torch.from_numpy(synth.pool_labeled(rows, int(os.environ.get("PROF_LABELLED", rows // 10)))).to(dev)
+    md = torch.empty(rows, dtype=torch.float64, device=dev)
+    print("tc init", ops.coreset_init_tc(X, lab, md, 0, rows)[:2])

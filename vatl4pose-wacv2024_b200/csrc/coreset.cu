@@ -790,38 +790,68 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   const int nt = ((long long)cid < ntiles) ? (int)((ntiles - cid + ncl - 1) / ncl) : 0;
   // tile j of the streamed sequence is tile k = tile_of(j) of the walker (rows (cid + k*ncl)*8 ...)
   const bool use_list = a.seg_skip != nullptr && a.prune_mode != 0 && nt <= kMaxTilesCta;
-  if (warp == kSeg + 1) {
-    int na = 0;
-    if (use_list) {
-      for (int base = 0; base < nt; base += 32) {
-        const int k = base + lane;
-        bool flagged = false;
-        if (k < nt) {
-          const long long r0 = ((long long)cid + (long long)k * ncl) * 8;   // relative to a.lo
-          const long long r1 = min(r0 + 7, a.hi - a.lo - 1);
-          const int s0 = a.seg_of_row[r0], s1 = a.seg_of_row[r1];
-          flagged = true;
-          for (int sg = s0; sg <= s1; ++sg) {
-            flagged = flagged && (a.seg_skip[sg] != 0);
-            if (PAIR) flagged = flagged && (a.seg_skip[a.skip_stride + sg] != 0);   // ... for BOTH centre groups
-          }
+  // The list of streamed tiles is built by ALL warps (chunks of 32 tiles dealt round-robin: the two dependent loads per
+  // tile — segment ids, then their flags — are one memory round trip per chunk instead of one per 32 tiles of the
+  // whole CTA); the chunk counts are scanned by one warp and every warp then writes its chunks at their offsets.
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_part);   // [kMaxTilesCta / 32] chunk counts (the partial buffers are idle)
+  constexpr int kWarps = kWsThreads / 32;
+  unsigned my_sm[(kMaxTilesCta / 32 + kWarps - 1) / kWarps];
+  if (use_list) {
+    int ci = 0;
+    for (int base = warp * 32; base < nt; base += kWarps * 32, ++ci) {
+      const int k = base + lane;
+      bool flagged = false;
+      if (k < nt) {
+        const long long r0 = ((long long)cid + (long long)k * ncl) * 8;   // relative to a.lo
+        const long long r1 = min(r0 + 7, a.hi - a.lo - 1);
+        const int s0 = a.seg_of_row[r0], s1 = a.seg_of_row[r1];
+        flagged = true;
+        for (int sg = s0; sg <= s1; ++sg) {
+          flagged = flagged && (a.seg_skip[sg] != 0);
+          if (PAIR) flagged = flagged && (a.seg_skip[a.skip_stride + sg] != 0);   // ... for BOTH centre groups
         }
-        const unsigned fm = __ballot_sync(0xffffffffu, flagged);
-        if (lane == 0) s_flagged[base >> 5] = fm;
-        const bool stream = (k < nt) && !(flagged && a.prune_mode == 1);
-        const unsigned sm = __ballot_sync(0xffffffffu, stream);
-        if (stream) s_tiles[na + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)k;
-        na += __popc(sm);
       }
-    } else {
-      na = nt;
+      const unsigned fm = __ballot_sync(0xffffffffu, flagged);
+      const bool stream = (k < nt) && !(flagged && a.prune_mode == 1);
+      const unsigned sm = __ballot_sync(0xffffffffu, stream);
+      my_sm[ci] = sm;
+      if (lane == 0) {
+        s_flagged[base >> 5] = fm;
+        s_cnt[base >> 5] = __popc(sm);
+      }
     }
-    if (lane == 0) {
-      *s_na = na;
-      if (a.prune_stats && nt > 0 && crank == 0) {
-        atomicAdd(&a.prune_stats[0], (unsigned long long)nt);
-        atomicAdd(&a.prune_stats[1], (unsigned long long)na);
+    __syncthreads();
+    if (warp == 0) {                     // exclusive scan of the chunk counts (<= 64 chunks: two per lane)
+      const int nch = (nt + 31) >> 5;
+      const unsigned c0 = (2 * lane < nch) ? s_cnt[2 * lane] : 0u, c1 = (2 * lane + 1 < nch) ? s_cnt[2 * lane + 1] : 0u;
+      unsigned incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
+      const unsigned excl = incl - (c0 + c1);
+      if (2 * lane < nch) s_cnt[2 * lane] = excl;
+      if (2 * lane + 1 < nch) s_cnt[2 * lane + 1] = excl + c0;
+      if (lane == 31) {
+        *s_na = (int)incl;
+        if (a.prune_stats && nt > 0 && crank == 0) {
+          atomicAdd(&a.prune_stats[0], (unsigned long long)nt);
+          atomicAdd(&a.prune_stats[1], (unsigned long long)incl);
+        }
+      }
+    }
+    __syncthreads();
+    ci = 0;
+    for (int base = warp * 32; base < nt; base += kWarps * 32, ++ci) {
+      const unsigned sm = my_sm[ci];
+      if ((sm >> lane) & 1u) s_tiles[s_cnt[base >> 5] + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)(base + lane);
+    }
+  } else if (threadIdx.x == 0) {
+    *s_na = nt;
+    if (a.prune_stats && nt > 0 && crank == 0) {
+      atomicAdd(&a.prune_stats[0], (unsigned long long)nt);
+      atomicAdd(&a.prune_stats[1], (unsigned long long)nt);
     }
   }
   __syncthreads();
@@ -1313,11 +1343,10 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
     else dmma_block<false, false>(X4 + (size_t)ridx * d4, d4, nss, s_c, S, lane, c);
     if (r0 + g < v.total) {
       const double xxi = xx[ridx];
-      const size_t row = (size_t)(r0 + g) * kCap;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 2; ++e) {   // Dcc[w * kCap + c] = d(row c, centre w): stored by CENTRE so that the planner reads a row
         const int col = col0 + 2 * kk + e;
-        if (col < v.total) Dcc[row + col] = dist_from_dot(c[e], xxi, s_xxc[2 * kk + e]);
+        if (col < v.total) Dcc[(size_t)col * kCap + (r0 + g)] = dist_from_dot(c[e], xxi, s_xxc[2 * kk + e]);
       }
     }
   }
@@ -1326,11 +1355,14 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
 __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double* Dcc, unsigned int* hist,
                           long long* out_idx, Ctl* ctl);
 
+// Candidate x candidate distances, symmetric: only the tile pairs (column block cb <= row tile t) are computed and
+// every 8 x 8 block is written twice (d is symmetric; both halves hold the SAME bits, so the planner may read rows).
+// The pairs are dealt round-robin to the CTAs of the grid: with ~250 candidates that is 528 pairs over 148 CTAs
+// (3-4 each, all loads of a pair in flight together) instead of 8 sequential tiles per CTA on a quarter of the SMs.
 template <int STEPS>
 __device__ __forceinline__ void pairs_tiles(const float* __restrict__ X, int d4, const double* __restrict__ xx,
                                             const RankBlock* blocks, const CandView& v, int world,
                                             double* __restrict__ Dcc, double (*s_part)[kSeg][64], double* s_xxc) {
-  const int col0 = blockIdx.x * kB;
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, g = lane >> 2, kk = lane & 3;
   const float4* X4 = reinterpret_cast<const float4*>(X);
   const int lane_off = seg * (STEPS * 4) + kk;
@@ -1339,32 +1371,27 @@ __device__ __forceinline__ void pairs_tiles(const float* __restrict__ X, int d4,
     locate(v, world, min(pos, v.total - 1), r, q);
     return blocks[r].idx[q];
   };
-  double breg[STEPS][4];
-  {
-    const float4* cp = X4 + (size_t)cand_row(col0 + g) * d4 + lane_off;
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      const float4 c4 = __ldg(cp + 4 * s);
-      breg[s][0] = (double)c4.x;
-      breg[s][1] = (double)c4.y;
-      breg[s][2] = (double)c4.z;
-      breg[s][3] = (double)c4.w;
-    }
-  }
-  if (threadIdx.x < kB) s_xxc[threadIdx.x] = xx[cand_row(col0 + threadIdx.x)];
-  const int ntiles = (v.total + 7) / 8;
-  int t = blockIdx.y;
-  float4 ring[STEPS];
-  if (t < ntiles) {
-    const float4* p0 = X4 + (size_t)cand_row(t * 8 + g) * d4 + lane_off;
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) ring[s] = __ldg(p0 + 4 * s);
-  }
+  const int nt = (v.total + 7) / 8;
+  const int npairs = nt * (nt + 1) / 2;
+  const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
   int buf = 0;
-  for (; t < ntiles; t += gridDim.y) {
-    const int tn = t + gridDim.y;
-    const bool has_next = tn < ntiles;
-    const float4* np = X4 + (size_t)cand_row((has_next ? tn : t) * 8 + g) * d4 + lane_off;
+  for (int p = cta; p < npairs; p += ncta) {
+    int cb = 0, q = p;                                   // p -> (cb, t), cb <= t
+    while (q >= nt - cb) {
+      q -= nt - cb;
+      ++cb;
+    }
+    const int t = cb + q, col0 = cb * kB;
+    // both operand tiles are requested back to back: one memory round trip per pair
+    const long long crow = cand_row(col0 + g), arow = cand_row(t * 8 + g);
+    const float4* cp = X4 + (size_t)crow * d4 + lane_off;
+    const float4* ap = X4 + (size_t)arow * d4 + lane_off;
+    float4 cb4[STEPS], ring[STEPS];
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) cb4[s] = __ldg(cp + 4 * s);
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) ring[s] = __ldg(ap + 4 * s);
+    if (threadIdx.x < kB) s_xxc[buf * kB + threadIdx.x] = xx[cand_row(col0 + threadIdx.x)];
     const int myrow = t * 8 + seg;                       // the row this warp finishes
     const double xxi = (myrow < v.total) ? xx[cand_row(myrow)] : 0.0;
     double c[4][2];
@@ -1372,19 +1399,22 @@ __device__ __forceinline__ void pairs_tiles(const float* __restrict__ X, int d4,
     for (int e = 0; e < 4; ++e) c[e][0] = c[e][1] = 0.0;
 #pragma unroll
     for (int s = 0; s < STEPS; ++s) {
-      const float4 x = ring[s];
-      if (has_next) ring[s] = __ldg(np + 4 * s);
-      dmma(c[0], (double)x.x, breg[s][0]);
-      dmma(c[1], (double)x.y, breg[s][1]);
-      dmma(c[2], (double)x.z, breg[s][2]);
-      dmma(c[3], (double)x.w, breg[s][3]);
+      dmma(c[0], (double)ring[s].x, (double)cb4[s].x);
+      dmma(c[1], (double)ring[s].y, (double)cb4[s].y);
+      dmma(c[2], (double)ring[s].z, (double)cb4[s].z);
+      dmma(c[3], (double)ring[s].w, (double)cb4[s].w);
     }
     *reinterpret_cast<double2*>(&s_part[buf][seg][lane * 2]) =
         make_double2(combine4(c[0][0], c[1][0], c[2][0], c[3][0]), combine4(c[0][1], c[1][1], c[2][1], c[3][1]));
     __syncthreads();
     if (myrow < v.total && lane < kB && col0 + lane < v.total) {
+      // Dcc[w * kCap + c] = d(row c, centre w) with the pass's operand roles (sklearn: (-2 x.c + |x|^2) + |c|^2, the
+      // two norms are NOT interchangeable in the last bit): the dot product is symmetric bit for bit (same products,
+      // same order), so one tile yields both orientations exactly.  The planner reads row w = the picked centre.
       const double dot = combine8(&s_part[buf][0][seg * 8 + lane], 64);
-      Dcc[(size_t)myrow * kCap + col0 + lane] = dist_from_dot(dot, xxi, s_xxc[lane]);
+      const double xxo = s_xxc[buf * kB + lane];
+      Dcc[(size_t)(col0 + lane) * kCap + myrow] = dist_from_dot(dot, xxi, xxo);   // row = myrow,   centre = col
+      Dcc[(size_t)myrow * kCap + col0 + lane] = dist_from_dot(dot, xxo, xxi);     // row = col,     centre = myrow
     }
     buf ^= 1;
   }
@@ -1404,7 +1434,7 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
                                                                   Ctl* ctl, double* __restrict__ Dcc, Mailbox* mail,
                                                                   unsigned long long seq) {
   __shared__ __align__(16) double s_part[2][kSeg][64];
-  __shared__ double s_xxc[kB];
+  __shared__ double s_xxc[2 * kB];
   __shared__ unsigned int s_last;
   if (ctl->n_picked >= ctl->k) {       // (uniform over the grid: nobody takes a ticket)
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctl->nb = 0;
@@ -1425,7 +1455,7 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
   {
     const int world = ctl->world;
     const CandView v = view_of(blocks, world);
-    if (!v.fallback && (int)blockIdx.x * kB < v.total) pairs_tiles<STEPS>(X, d4, xx, blocks, v, world, Dcc, s_part, s_xxc);
+    if (!v.fallback) pairs_tiles<STEPS>(X, d4, xx, blocks, v, world, Dcc, s_part, s_xxc);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1664,7 +1694,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
       out_idx[ctl->n_picked + nb] = win.i;
     }
     nb += 1;
-    const double* drow = Dcc + (size_t)wpos * kCap;   // d is symmetric: the winner's row, coalesced
+    const double* drow = Dcc + (size_t)wpos * kCap;   // drow[c] = d(row c, centre = the winner), coalesced
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
       const int c = tid + kPlanThreads * j;
@@ -2213,7 +2243,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       if (nbk > 1) {
         dim3 pg(kCap / kB, 4);
         if (fast_d) {
-          pairs_plan_kernel<16><<<pg, kSeg * 32, 0, stream>>>(X, G.d4, xx, blocks, send, hist, (long long*)out_idx, ctl, Dcc,
+          pairs_plan_kernel<16><<<dim3((unsigned)sm_count(), 1), kSeg * 32, 0, stream>>>(X, G.d4, xx, blocks, send, hist, (long long*)out_idx, ctl, Dcc,
                                                              mail, seq0 + round_no);
         } else {
           if (p2p) wait_blocks_kernel<<<1, 1, 0, stream>>>(mail, ctl, seq0 + round_no);

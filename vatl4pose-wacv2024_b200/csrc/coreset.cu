@@ -2152,7 +2152,13 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       const int t = e ? atoi(e) : 0;
       return (t >= 16 && t <= kCap) ? t : 0;
     }();
-    h.target = target ? target : (nbk > kB ? kTarget + kTarget / 2 : kTarget);   // 16 picks per round want a longer list
+    // wanted candidates per round (all ranks together).  The candidate x candidate tiles and the planner cost grow with
+    // the square of the list while a short list ends rounds early: measured on B200 (tools/round_cost.py, 16 picks per
+    // round) 192 is best for 64 k .. 300 k rows per rank, 256 above, 384 for small pools.  n / world is the same on
+    // every rank.
+    const long long per_rank = n / std::max(1, world);
+    const int t16 = n < 65536 ? kTarget + kTarget / 2 : (per_rank <= 300000 ? 192 : 256);
+    h.target = target ? target : (nbk > kB ? t16 : kTarget);
   }
   if (n_labeled == 0 && rule == 2) {
     // _query (:828-833): the caller drew the random first pick

@@ -140,7 +140,8 @@ int vatlq_fuse_final(const uint8_t* unlabeled, int64_t n, const double* stats2,
  * anyway): [0] passes over X, [1] picks, [2] rounds planned, [3] fallback rounds (nothing listed),
  * [4] fallback rounds (list overflow), [5] sum of candidates, [6] rounds launched, [7] picks per
  * round, [8..10] ns spent waiting for the peers' candidate blocks / in the candidate x candidate
- * tiles / in the planner (summed over the rounds), [11..15] reserved.
+ * tiles / in the planner (summed over the rounds), [11..14] this call's pruning statistics: tiles seen,
+ * tiles streamed, verify violations, segments; [15] reserved.
  * ------------------------------------------------------------------------------------ */
 size_t vatlq_coreset_workspace_bytes(int64_t n, int d, int batch);
 int vatlq_coreset_init(const float* X, int64_t n, int d, int64_t row_lo, int64_t row_hi,

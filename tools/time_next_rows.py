@@ -28,6 +28,14 @@ out = {}
 H, ip, inx, bb = synth.device_pool(frames, dev, seed=1)
 t = timed(lambda: ops.heatmap_entropy(H))
 out["entropy"] = {"frames": frames, "ms": t * 1e3, "GBps": frames * 17 * 64 * 48 * 4 / t / 1e9}
+t = timed(lambda: ops.peak_uncertainty(H))
+out["mpe_margin"] = {"frames": frames, "ms": t * 1e3, "GBps": frames * 17 * 64 * 48 * 4 / t / 1e9}
+sc = torch.rand(rows, dtype=torch.float64, device=dev)
+t = timed(lambda: ops.rank_scores(sc))
+out["rank_scores"] = {"rows": rows, "ms": t * 1e3}
+kp = torch.rand((rows, 17, 3), device=dev) * 100
+t = timed(lambda: ops.oks(kp, kp + 1.0, torch.tensor([[0., 0., 99., 199.]], device=dev).repeat(rows, 1)))
+out["oks"] = {"rows": rows, "ms": t * 1e3}
 r = ops.heatmap_scan(H, ip, inx, bb)
 t = timed(lambda: ops.pose_uncertainty(r.coords_hm, r.kpts, bb, ip, inx))
 out["hp_tpc"] = {"frames": frames, "ms": t * 1e3}

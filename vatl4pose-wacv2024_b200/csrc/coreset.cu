@@ -140,11 +140,13 @@ __device__ void push_block(const PushArgs& p, const RankBlock* send) {
 }
 
 // thread 0 of a CTA waits until every rank's block `seq` has landed in the local mailbox
+__device__ long long g_mail_timeout_clk = 60000000000LL;   // ~30 s at 2 GHz (VATLQ_MAILBOX_TIMEOUT_S, set at comm attach)
 __device__ __forceinline__ void wait_blocks(Mailbox* mine, int world, unsigned long long seq) {
   const long long t0 = clock64();
+  const long long limit = g_mail_timeout_clk;
   for (int r = 0; r < world; ++r) {
     while (*((volatile unsigned long long*)&mine->flags[r]) < seq) {
-      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; report instead of hanging the GPU
+      if (clock64() - t0 > limit) {   // a peer died (or was held up for longer than the limit): report instead of hanging the GPU
         mine->error = seq;
         return;
       }
@@ -2123,6 +2125,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   RankBlock* recv = (world > 1) ? (RankBlock*)(w + L.recv) : send;
   const bool p2p = world > 1 && comm->peers_dev != nullptr;   // peer-memory mailbox instead of ncclAllGather
   const unsigned long long seq0 = p2p ? comm->seq : 0ULL;
+  if (p2p) VQ_CUDA(cudaMemsetAsync(&comm->mail->error, 0, 8, stream));   // a past time-out must not fail this call
   auto push_of = [&](unsigned long long seq) {
     PushArgs pa{};
     if (p2p) {
@@ -2222,8 +2225,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   long long rounds_done = 0;
   long long passes_seen = (n_labeled == 0 && rule == 2) ? 1 : 0;
   g_prof.used = 0;
-  long long* h_picked = nullptr;
-  VQ_CUDA(cudaMallocHost(&h_picked, sizeof(Ctl)));
+  Ctl h_ctl{};                      // host copy of the control block, refreshed every chunk of rounds
+  Ctl* h_picked = &h_ctl;
   int rc = 0;
   while (picked < k && rc == 0) {
     const long long remaining = k - picked;
@@ -2358,8 +2361,14 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     host_stats[8] = (int64_t)hc->stat_ns_wait;
     host_stats[9] = (int64_t)hc->stat_ns_tiles;
     host_stats[10] = (int64_t)hc->stat_ns_plan;
+    PruneCtl hp{};     // this call's tiles seen / streamed / verify violations / segments (no process-wide state needed)
+    if (cudaMemcpy(&hp, P.pc, sizeof(PruneCtl), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      host_stats[11] = (int64_t)hp.stats[0];
+      host_stats[12] = (int64_t)hp.stats[1];
+      host_stats[13] = (int64_t)hp.stats[2];
+      host_stats[14] = hp.nseg;
+    }
   }
-  cudaFreeHost(h_picked);
   return rc;
 }
 
@@ -2472,6 +2481,13 @@ extern "C" int vatlq_comm_attach(void* comm, const void* host_handles, int world
     }
     cm->opened[r] = p;
     ptrs[r] = (Mailbox*)p;
+  }
+  if (const char* e = getenv("VATLQ_MAILBOX_TIMEOUT_S")) {
+    const double sec = atof(e);
+    if (sec > 0.0) {
+      const long long clk = (long long)(sec * 2.0e9);
+      VQ_CUDA(cudaMemcpyToSymbol(g_mail_timeout_clk, &clk, sizeof(clk)));
+    }
   }
   VQ_CUDA(cudaMalloc((void**)&cm->peers_dev, sizeof(Mailbox*) * kMaxRanks));
   VQ_CUDA(cudaMemcpy(cm->peers_dev, ptrs, sizeof(Mailbox*) * kMaxRanks, cudaMemcpyHostToDevice));

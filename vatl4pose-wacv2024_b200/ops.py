@@ -212,6 +212,10 @@ class CoresetStats:
     ns_wait: int = 0        # waiting for the peers' candidate blocks (summed over the rounds)
     ns_tiles: int = 0       # candidate x candidate distance tiles
     ns_plan: int = 0        # the planner (greedy replay on the candidates)
+    tiles: int = 0          # 8-row tiles the passes of this call saw ...
+    tiles_streamed: int = 0  # ... and streamed (the rest was pruned exactly)
+    prune_violations: int = 0   # verify mode only: rows of flagged tiles whose min_d moved (must be 0)
+    segments: int = 0
 
 
 TC_INIT_MIN_LABELED = 256     # below this the exact passes are cheaper than two GEMM sweeps
@@ -279,7 +283,7 @@ def coreset_select(X: torch.Tensor, unc: torch.Tensor, labeled, k: int, moks: fl
                                           C.c_void_p(comm) if comm else None, _ptr(ws), ws_bytes,
                                           C.cast(stats, C.c_void_p), _stream()), "vatlq_coreset_select")
     picks = out[:k]
-    st = CoresetStats(*[int(v) for v in stats][:11])
+    st = CoresetStats(*[int(v) for v in stats][:15])
     if return_state:
         return picks, st, min_d, unc
     return picks, st

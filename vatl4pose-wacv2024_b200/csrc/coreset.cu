@@ -346,6 +346,12 @@ struct PassArgs {
   const int* seg_of_row;             // [owned row] -> segment id, or null
   size_t skip_stride;                // paired pass: the flags of centre group 1 start at seg_skip + skip_stride
   const unsigned char* seg_skip;     // [segment] 1: no row of the segment can get closer to this pass's centres
+  // filter mode (pass_kernel_tma<.., FILTER = true>): the tiles are groups of 8 segment ANCHOR rows and the epilogue
+  // writes the segments' skip flags instead of dot products
+  const int* seg_start;              // [nseg + 1] first owned row of every segment
+  const double* seg_r;               // [nseg] segment radius
+  const int* nseg;                   // device count of segments
+  unsigned char* seg_skip_out;       // [2][skip_stride] flags written by the filter mode
   int prune_mode;                    // 0 off, 1 skip, 2 verify (stream everything, count rows that changed anyway)
   unsigned long long* prune_stats;   // [0] tiles seen, [1] tiles streamed, [2] verify violations
 };
@@ -734,7 +740,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int STEPS, bool PAIR>
+template <int STEPS, bool PAIR, bool FILTER = false>
 __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   static_assert(STEPS * 16 * kSeg * 4 + 64 == kRowBytesX, "stage geometry is for d = 2048");
   constexpr int NC = PAIR ? 2 * kB : kB;          // dot products per row the finishing reads
@@ -756,7 +762,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   const int crank = PAIR ? (int)cluster_ctarank() : 0;
   bool final_pass;
   int nb;
-  if (PAIR) {
+  if (PAIR && FILTER) {
+    nb = min(kB, total - kB * crank);              // group r's flags; a group without centres has nothing to do
+    final_pass = false;
+    if (nb <= 0) return;
+  } else if (PAIR) {
     if (total <= kB) return;                       // (both CTAs of the pair: the solo pass handles short rounds)
     nb = min(kB, total - kB * crank);
     final_pass = true;
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncl = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;       // independent tile walkers
   const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (!FILTER && blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.ctl) a.ctl->stat_passes += 1;
     if (a.did_work) *a.did_work = 1;
   }
@@ -788,10 +798,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const long long ntiles = (a.hi - a.lo + 7) / 8;
+  const int nseg = FILTER ? *a.nseg : 0;
+  const long long ntiles = FILTER ? (nseg + 7) / 8 : (a.hi - a.lo + 7) / 8;
   const int nt = ((long long)cid < ntiles) ? (int)((ntiles - cid + ncl - 1) / ncl) : 0;
   // tile j of the streamed sequence is tile k = tile_of(j) of the walker (rows (cid + k*ncl)*8 ...)
-  const bool use_list = a.seg_skip != nullptr && a.prune_mode != 0 && nt <= kMaxTilesCta;
+  const bool use_list = !FILTER && a.seg_skip != nullptr && a.prune_mode != 0 && nt <= kMaxTilesCta;
   // The list of streamed tiles is built by ALL warps (chunks of 32 tiles dealt round-robin: the two dependent loads per
   // tile — segment ids, then their flags — are one memory round trip per chunk instead of one per 32 tiles of the
   // whole CTA); the chunk counts are scanned by one warp and every warp then writes its chunks at their offsets.
@@ -923,7 +934,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
         if (lane == 0) mbar_expect_tx(&full[st], 8u * 2048u * 4u);
         __syncwarp();
         if (lane < 8) {
-          const long long row = min(a.lo + ((long long)cid + (long long)k * ncl) * 8 + lane, a.hi - 1);
+          long long row;
+          if (FILTER) row = a.lo + a.seg_start[min((int)(((long long)cid + (long long)k * ncl) * 8 + lane), nseg - 1)];   // anchor rows
+          else row = min(a.lo + ((long long)cid + (long long)k * ncl) * 8 + lane, a.hi - 1);
           tma_load_1d(stage0 + (size_t)st * kStageBytesX + lane * kRowBytesX, a.X + (size_t)row * 2048, 2048u * 4u, &full[st]);
         }
         if (++st == kStagesX) {
@@ -941,17 +954,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
         const double dot0 = combine8(&s_part[ew][0][lane * 2], 64);
         const double dot1 = combine8(&s_part[ew][0][lane * 2 + 1], 64);
         if (j + kPartBufs < na) named_arrive(1 + kPartBufs + ew, kSeg * 32 + 32);   // partials consumed
-        const long long row = ((long long)cid + (long long)k * ncl) * 8 + r;   // relative to a.lo
-        if (a.lo + row < a.hi)
+        const long long row = ((long long)cid + (long long)k * ncl) * 8 + r;   // relative to a.lo (FILTER: segment id)
+        if (FILTER) {
+          // segment `row`: nearest of this group's centres to its anchor, largest min_d of its rows, the test of
+          // "pruning (exact)" below — same arithmetic as prune_filter_kernel, on the pass's tile machine
+          const int kk = lane & 3, sg = (int)min(row, (long long)nseg - 1);
+          const int a0 = a.seg_start[sg], e0 = a.seg_start[sg + 1];
+          const double xxa = a.xx[a.lo + a0];
+          double sq = fmin(sq_from_dot(dot0, xxa, s_xxc[crank * kB + 2 * kk]), sq_from_dot(dot1, xxa, s_xxc[crank * kB + 2 * kk + 1]));
+          double M = 0.0;
+          for (int q = a0 + kk; q < e0; q += 4) M = fmax(M, a.m[a.lo + q]);
+          sq = fmin(sq, __shfl_xor_sync(0xffffffffu, sq, 1));
+          sq = fmin(sq, __shfl_xor_sync(0xffffffffu, sq, 2));
+          M = fmax(M, __shfl_xor_sync(0xffffffffu, M, 1));
+          M = fmax(M, __shfl_xor_sync(0xffffffffu, M, 2));
+          if (kk == 0 && row < nseg) {
+            double cn = 0.0;
+#pragma unroll
+            for (int jc = 0; jc < kB; ++jc) cn = fmax(cn, s_xxc[crank * kB + jc]);
+            const double margin = 1e-6 * (1.0 + sqrt(xxa) + sqrt(cn));
+            a.seg_skip_out[(size_t)crank * a.skip_stride + row] =
+                (isfinite(M) && sqrt(fmax(sq, 0.0)) - a.seg_r[row] - M >= margin) ? 1 : 0;
+          }
+        } else if (a.lo + row < a.hi) {
           *reinterpret_cast<double2*>(a.dots + row * NC + crank * kB + (lane & 3) * 2) = make_double2(dot0, dot1);
+        }
       }
-      if (PAIR) __threadfence();                  // the partner CTA reads these dot products
+      if (PAIR && !FILTER) __threadfence();       // the partner CTA reads these dot products
     }
   }
   // ---- apply phase: the walker's own rows (their dot products were written by its own epilogue
   // warps, visible after the barrier), one row per compute-warpgroup thread at a time; a pair splits
   // its rows by tile parity after the cluster barrier that makes both CTAs' dot products visible
   __syncthreads();
+  if (FILTER) return;                             // flags written; no rows to finish
   if (PAIR) cluster_sync_all();
   Best best{-INFINITY, 0x7fffffffffffffffLL};
   const ApplyConst ac = apply_const(a, final_pass);
@@ -1924,6 +1960,7 @@ static int configure_pass() {
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
     VQ_CUDA(cudaFuncSetAttribute(pass_kernel_tma<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
+    VQ_CUDA(cudaFuncSetAttribute((pass_kernel_tma<16, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmem));
     configured = true;
   }
   return 0;
@@ -1956,7 +1993,9 @@ static int pair_grid() {
 }
 
 // the paired pass of a 16-pick round (d = 2048 only): applies picks [0, nb) when nb > 8, reading X once
-static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+// (filter = true: the same tile machine over the segment anchors, writing both centre groups' skip flags)
+static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                            bool filter = false) {
   if (int e = configure_pass()) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)pair_grid());
@@ -1970,7 +2009,8 @@ static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = 
   cfg.attrs = &at;
   cfg.numAttrs = 1;
   if (ev0) cudaEventRecord(ev0, stream);
-  VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true>, a));
+  if (filter) VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true, true>, a));
+  else VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true, false>, a));
   if (ev1) cudaEventRecord(ev1, stream);
   VQ_LAUNCHED();
   return 0;
@@ -2182,6 +2222,11 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   const size_t pairs_smem = G.smem;
   const bool fast_d = (G.d4 == kSeg * 4 * 16);   // d = 2048: register-resident centres
   const bool use_pair = fast_d && nbk > kB && pair_grid() >= 2;   // 16 picks per round in one read of X
+  static const long long tma_filter_min = []() {
+    const char* e = getenv("VATLQ_TMA_FILTER_MIN_ROWS");
+    return e ? atoll(e) : 0LL;
+  }();
+  const bool tma_filter = (row_hi - row_lo) >= tma_filter_min;
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -2269,7 +2314,13 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       if (prune_mode) {   // flags of every centre group of the round in one launch
         PassArgs a{};
         fill_pass(a);
-        rc = launch_filter(P, a, stream, (nbk + kB - 1) / kB);
+        if (use_pair && tma_filter) {   // the pass's own TMA / DMMA tile machine over the anchor rows (bandwidth-bound)
+          a.seg_start = P.seg_start; a.seg_r = P.seg_r; a.nseg = &P.pc->nseg; a.seg_skip_out = P.seg_skip;
+          a.skip_stride = P.skip_stride;
+          rc = launch_pass_pair(a, stream, nullptr, nullptr, true);
+        } else {
+          rc = launch_filter(P, a, stream, (nbk + kB - 1) / kB);
+        }
       }
       auto timed_launch = [&](PassArgs& a, bool pair) {
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;

@@ -15,18 +15,16 @@ WANT = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "dur"), ("dram__by
         ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_cyc%"),
         ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_cyc%"),
-        ("sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_op_cyc%"),
-        ("sm__inst_executed_pipe_tensor_op_dmma.sum", "dmma_inst"),
-        ("sm__inst_executed_pipe_uniform.sum", "uniform_inst"),
+        ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem_inst%"),
+        ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tma_cyc%"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("launch__shared_mem_per_block_dynamic", "dsmem"), ("launch__shared_mem_per_block_static", "ssmem")]
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 cols = [(hdr.index(k), n) for k, n in WANT if k in hdr]
-extra = [(i, c) for i, c in enumerate(hdr) if ("tensor" in c or "tmem" in c or "utc" in c.lower()) and c not in dict(WANT)]
-if len(sys.argv) > 2 and sys.argv[2] == "--tensor":
-    cols += [(i, c.replace("sm__", "").replace(".avg.pct_of_peak_sustained_active", "%")[:40]) for i, c in extra]
+if len(sys.argv) > 2 and sys.argv[2] == "--tensor":     # list every tensor / TMEM metric name the report holds
+    print("# tensor-related metrics:", ", ".join(c for c in hdr if "tensor" in c or "tmem" in c))
 print("# " + sys.argv[1])
 print(" | ".join(f"{n}[{units[i]}]" if units[i] else n for i, n in cols))
 for r in rows[2:]:

@@ -466,9 +466,12 @@ extern "C" int vatlq_heatmap_entropy(const float* H, int64_t n, int J, int h, in
   VQ_REQUIRE((maps + 7) / 8 <= 2147483647LL, "grid too large");
   const int npx = h * w;
   const unsigned grid = (unsigned)((maps + 7) / 8);
+  // Measured on B200 (tools/time_next_rows.py, 40 000 frames): the TMA-staged variant runs at 2.5 TB/s, the
+  // register-staged one at 3.9 TB/s — the kernel is bound by the ~1.4 k instructions per lane and map (MUFU.LG2 chain),
+  // and 8 warps per SM (196 KB of stages) hide less of that than 16 resident warps do.  Kept for experiments only.
   static const bool use_tma = []() {
     const char* e = getenv("VATLQ_ENTROPY_TMA");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   if (npx == kEntPix && ((uintptr_t)H & 15) == 0 && use_tma && maps >= 4096) {
     static bool cfg = false;

@@ -591,7 +591,10 @@ def full_query(a, n, n_lab, k, moks, config, rank, world, local, dev):
                 "coreset": {"passes_over_X": st.passes, "picks": st.picks, "rounds": st.rounds,
                             "fallback_rounds": st.fallback_empty + st.fallback_overflow,
                             "mean_candidates": st.candidates / max(1, st.rounds - st.fallback_empty - st.fallback_overflow),
-                            "ms_per_round": (ms_step - scan_s * 1e3) / max(1, st.rounds)}}
+                            "ms_per_round": (ms_step - scan_s * 1e3) / max(1, st.rounds),
+                            "us_per_round": {"waiting_for_peer_blocks": st.ns_wait / 1e3 / max(1, st.rounds),
+                                             "candidate_tiles": st.ns_tiles / 1e3 / max(1, st.rounds),
+                                             "planner": st.ns_plan / 1e3 / max(1, st.rounds)}}}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(a, n, k, moks)
     if not same_all or (parity.get("pinned") and not parity.get("ok")):
@@ -616,6 +619,8 @@ def run_e2e(a, segs, ip, inx, bb, Xl, W, labeled, n, nl, k, moks, world, comm, d
         avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
     except Exception:
         avail = 64 << 30
+    if os.environ.get("VATLQ_BENCH_HOST_GB"):          # (tests of the reduced-ring path)
+        avail = int(float(os.environ["VATLQ_BENCH_HOST_GB"]) * (1 << 30) / 0.4) * max(1, world)
     budget_frames = max(chunk, int(0.4 * avail / max(1, world) / FRAME_BYTES) // chunk * chunk)
     # pinned host copies of the distinct heat-map buffers (segments that view one ring share one host copy)
     uniq = {}

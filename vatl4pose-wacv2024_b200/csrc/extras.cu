@@ -86,10 +86,13 @@ __global__ void __launch_bounds__(128) oks_kernel(const float* __restrict__ kpts
 constexpr int kPeakWarps = 4;
 constexpr int kPeakMinDist = 5;
 
+// CH / CW > 0: compile-time map shape (64 x 48: index arithmetic without runtime divisions), else the arguments
+template <int CH, int CW>
 __global__ void __launch_bounds__(kPeakWarps * 32)
-peak_unc_kernel(const float* __restrict__ H, long long maps, int h, int w, float* __restrict__ mpe_map,
+peak_unc_kernel(const float* __restrict__ H, long long maps, int h_, int w_, float* __restrict__ mpe_map,
                 float* __restrict__ margin_map) {
-  extern __shared__ float s_peak[];
+  const int h = CH > 0 ? CH : h_, w = CW > 0 ? CW : w_;
+  extern __shared__ __align__(16) float s_peak[];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long mi = (long long)blockIdx.x * kPeakWarps + wp;
   if (mi >= maps) return;
@@ -98,10 +101,21 @@ peak_unc_kernel(const float* __restrict__ H, long long maps, int h, int w, float
   float* aux = img + npx;                         // row maxima, then the peak mask (as 0 / 1)
   const float* src = H + (size_t)mi * npx;
   float vmin = INFINITY;
-  for (int i = lane; i < npx; i += 32) {
-    const float v = __ldg(src + i);
-    img[i] = v;
-    vmin = fminf(vmin, v);
+  if (CH > 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(img);
+#pragma unroll 4
+    for (int i = lane; i < npx / 4; i += 32) {
+      const float4 v = ldg_stream(s4 + i);
+      d4[i] = v;
+      vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+    }
+  } else {
+    for (int i = lane; i < npx; i += 32) {
+      const float v = __ldg(src + i);
+      img[i] = v;
+      vmin = fminf(vmin, v);
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
@@ -322,11 +336,14 @@ extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, fl
   VQ_REQUIRE(smem <= 200 * 1024, "map too large for the shared-memory staging");
   static size_t configured = 0;
   if (smem > configured) {
-    VQ_CUDA(cudaFuncSetAttribute(peak_unc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQ_CUDA(cudaFuncSetAttribute((peak_unc_kernel<0, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQ_CUDA(cudaFuncSetAttribute((peak_unc_kernel<64, 48>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   float* mm = (float*)ws;
-  peak_unc_kernel<<<(unsigned)((maps + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
+  const unsigned pgrid = (unsigned)((maps + kPeakWarps - 1) / kPeakWarps);
+  if (h == 64 && w == 48) peak_unc_kernel<64, 48><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
+  else peak_unc_kernel<0, 0><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
   VQ_LAUNCHED();
   peak_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mm, mm + maps, (long long)n, J, mpe, margin);
   VQ_LAUNCHED();

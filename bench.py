@@ -211,13 +211,16 @@ def cpu_reference_arm(config: int, n_pool: int, k: int, moks: float, cpu_frames:
 
 
 def ncu_traffic(kernel: str, rows: int):
-    """dram__bytes_read+write per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json), valid only for the shape it was captured at; else None."""
+    """dram__bytes_read+write per launch of `kernel` from the committed ncu captures (profiles/ncu_traffic.json),
+    valid only for the shape it was captured at (an entry is quoted when its `rows` equals this rank's); else None."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
-        return t["bytes_per_launch"] if int(t["rows"]) == int(rows) else None
+        for e in (t if isinstance(t, list) else [t]):
+            if int(e["rows"]) == int(rows):
+                return e["bytes_per_launch"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 def golden_for(config: int, n: int, lab_frac: float, moks: float, kind: str):

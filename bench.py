@@ -266,7 +266,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if a.batch is None:
-        a.batch = 16    # two 8-centre passes per round: measured best at every GPU count once the passes are pruned
+        a.batch = 16    # 16 picks per round: one paired pass (two CTAs per tile, 8 centres each) per read of X
     n = a.frames if a.frames is not None else CONFIG_FRAMES[a.config]
     n_lab = int(n * a.labeled_frac)
     k = int(n * (a.labeled_frac + a.query_frac)) - n_lab

@@ -12,7 +12,12 @@ Pinning: every function below is compared BIT-FOR-BIT against the reference's ow
 (imported from /root/reference with import stubs) by `oracle/pin_against_reference.py`,
 which also writes the golden fixtures under `tests/golden/`.  The reference ships no tests
 or golden vectors for this path, so the pin is "outputs of the reference
-itself run in the build container".
+itself run in the build container".  At BASELINE scale (100 000 .. 1 000 000 items) the selection is
+pinned by `oracle/pin_scale.py`, which runs the reference's own `coreset_selection` on the pools the
+benchmark uses (`tests/golden/coreset_scale_*.npz`).
+ONE EXCEPTION — PARITY UNPINNED: `peak_local_max` below restates scikit-image 0.24's published algorithm
+(scikit-image is not installed in the build container); MPE / Margin are pinned through the reference's own
+`compute_mpe` / `compute_margin` calling that restatement, not against the library itself.
 
 Citations are `path:line` relative to the reference root.
 """

@@ -11,12 +11,15 @@
 // can be decided in advance on the candidate set {score >= theta}: as long as the best
 // surviving candidate still scores >= theta it beats every non-candidate (all < theta), ties
 // resolving to the lowest index exactly like np.argmax.  One pass over X then applies up to
-// kB picks at once, reading every row of X from HBM once instead of kB times.
+// 16 picks at once, reading the rows it streams from HBM once instead of 16 times.
 //
-// A round is three kernels: pairs (candidate x candidate distances) -> plan (replays the greedy
-// rule on the candidates, emits <= kB picks, chooses the next theta from the score histogram)
-// -> pass (applies the picks to every owned row; its epilogue lists the next candidates, the
-// exact arg-max for the fallback and the next histogram, so no separate filter pass exists).
+// A round (d = 2048, up to 16 picks) is: pairs_plan_kernel (candidate x candidate distances, symmetric
+// tiles; its last CTA replays the greedy rule on the candidates, emits the picks and chooses the next
+// theta from the score histogram) -> the segment filter (exact pruning flags of both centre groups: the
+// FILTER mode of the pass kernel on the segment anchors) -> the paired pass (a cluster of two CTAs
+// applies 16 picks per read of X; its epilogue lists the next candidates, the exact arg-max for the
+// fallback and the next histogram, and pushes the rank's block to the peers' mailboxes).  Rounds of
+// <= 8 picks take the solo pass.  Other feature widths use the generic kernels (pairs / plan / pass).
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -186,7 +189,7 @@ __device__ __forceinline__ double dist_from_dot(double dot, double xxi, double x
 // Every kernel (norms, pass, candidate pairs, pairwise) evaluates exactly this, so d(i,c) has
 // the same bits wherever it is computed and dot(x,x) == xx (d(c,c) == 0).  In the pass the eight
 // segments of a block are computed by eight warps in parallel (split-K): a warp then only ever
-// needs 1/8 of every centre, which fits its REGISTERS (see pass_kernel_reg).
+// needs 1/8 of every centre, which fits its REGISTERS (see pass_kernel_tma).
 constexpr int kSeg = 8;
 #ifndef VQ_DEPTH
 #define VQ_DEPTH 8
@@ -338,7 +341,7 @@ struct PassArgs {
   Best* partial;             // per-CTA arg-max scratch (gridDim entries)
   PushArgs push;             // push.peers != null: the published block is pushed to every rank's mailbox
   unsigned char* did_work;   // optional: set to 1 when this launch applied centres (pass timing bookkeeping)
-  double* dots;              // fast path: [owned row][kB] canonical dot products, pass_kernel_ws -> apply_kernel
+  double* dots;              // fast path: [owned row][8 or 16] canonical dot products: epilogue warps -> row finishing
   // exact pruning (fast path only, see "pruning" below): tiles whose segments were all flagged by
   // prune_filter_kernel are not streamed; their rows keep min_d and only take part in the epilogue
   int only_if_le8;           // solo pass of a 16-pick round: run only when the round planned <= 8 picks (else the

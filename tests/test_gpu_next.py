@@ -250,3 +250,23 @@ def test_rank_scores_equals_python_stable_sort(built_lib):
         assert v.ops.rank_scores(torch.from_numpy(s).cuda(), torch.from_numpy(mask).cuda(), descending=desc, count=17).cpu().tolist() == expect[:17]
     allrows = v.ops.rank_scores(torch.from_numpy(s).cuda()).cpu().tolist()
     assert allrows == [i for i, _ in sorted(enumerate(s), key=lambda x: x[1], reverse=True)]
+
+
+def test_new_rows_edge_shapes(built_lib):
+    """Empty and single-item inputs; MPE / Margin on a non-64x48 map shape (generic path) against the oracle."""
+    from oracle import vatl_oracle as O
+    v = built_lib
+    dev = "cuda:0"
+    assert v.ops.oks(torch.zeros((0, 17, 3), device=dev), torch.zeros((0, 17, 3), device=dev), torch.zeros((0, 4), device=dev)).numel() == 0
+    assert v.ops.rank_scores(torch.tensor([0.5], dtype=torch.float64, device=dev)).cpu().tolist() == [0]
+    assert v.ops.rank_scores(torch.zeros(0, dtype=torch.float64, device=dev)).numel() == 0
+    rng = np.random.default_rng(8)
+    H = rng.normal(0, 0.05, (3, 5, 40, 30)).astype(np.float32)
+    H[0, 0, 20, 15] = 1.0; H[0, 0, 8, 8] = 0.7; H[1, 2] = 0.3      # peaks; a constant (trivial) map
+    mpe, mar = v.ops.peak_uncertainty(torch.from_numpy(H).to(dev))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_mpe = [O.mpe_item(H[i]) for i in range(3)]
+        ref_mar = [O.margin_item(H[i]) for i in range(3)]
+    assert np.allclose(mpe.cpu().numpy(), ref_mpe, rtol=1e-5, atol=1e-6)
+    assert np.allclose(mar.cpu().numpy(), ref_mar, rtol=1e-5, atol=1e-6)

@@ -80,3 +80,19 @@ def test_selection_uses_tc_init_and_picks_are_unchanged(built_lib):
     assert v.ops._tc_init_stats["calls"] == before["calls"] + 1
     p_ex, _, md_ex, _ = v.ops.coreset_select(X, unc, labh, 300, 0.6, 0.01, return_state=True, tc_init=False)
     assert torch.equal(p_tc, p_ex) and torch.equal(md_tc, md_ex)
+
+
+def test_tc_init_small_and_ragged_shapes(built_lib):
+    """Fewer rows than one 128-row tile, a ragged last tile, L not a multiple of 8, duplicate labelled rows."""
+    v = built_lib
+    dev = torch.device("cuda:0")
+    for n, L in ((100, 16), (300, 260), (1000, 257)):
+        X = v.synth.pool_embeddings(n, kind="clustered", device=dev)
+        lab_h = v.synth.pool_labeled(n, L)
+        if L >= 2:
+            lab_h[1] = lab_h[0]            # a duplicate centre
+        lab = torch.from_numpy(lab_h).to(dev)
+        md = torch.full((n,), -1.0, dtype=torch.float64, device=dev)
+        ok, st, _ = v.ops.coreset_init_tc(X, lab, md, 0, n, verify=True)
+        assert ok and st["violations"] == 0
+        assert torch.equal(md, _exact_init(v, X, lab, 0, n))

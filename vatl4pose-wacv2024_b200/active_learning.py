@@ -354,7 +354,7 @@ class ActiveLearning:
             # the NEXT query (moks_queried) and the stopping criteria come from it
             gt, bann = (batch[4], batch[8]) if len(batch) > 8 else (None, None)
             if gt is not None and bann is not None and self.oks_fn is None:
-                gt_t = torch.as_tensor(np.asarray(gt), dtype=torch.float32).reshape(b, -1)
+                gt_t = torch.as_tensor(np.asarray(gt), dtype=torch.float32).reshape(b, 51)
                 ba_t = torch.as_tensor(np.asarray(bann), dtype=torch.float32).reshape(b, 4)
                 oks_dev[pos:pos + b] = ops.oks(qp.kpts[pos:pos + b], gt_t, ba_t)
             else:

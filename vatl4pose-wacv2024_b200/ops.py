@@ -434,7 +434,7 @@ def oks(kpts: torch.Tensor, gt_kpts: torch.Tensor, bbox_ann_xyxy: torch.Tensor) 
     kpts = _cuda(kpts, torch.float32, "kpts")
     n = kpts.shape[0]
     dev = kpts.device
-    gt = _cuda(gt_kpts.to(dev).reshape(n, -1), torch.float32, "gt_kpts")
+    gt = _cuda(gt_kpts.to(dev).reshape(n, 51), torch.float32, "gt_kpts")
     bb = _cuda(bbox_ann_xyxy.to(dev).reshape(n, 4), torch.float32, "bbox_ann_xyxy")
     if kpts.numel() != n * 51 or gt.numel() != n * 51:
         raise _lib.VatlqError("kpts and gt_kpts must be (n,17,3)")

@@ -73,6 +73,8 @@ struct Ctl {
   long long stat_passes, stat_rounds, stat_fallback_empty, stat_fallback_overflow, stat_cand_sum;
   // where a round's planning time goes (ns, %globaltimer; summed over the rounds of a call)
   unsigned long long t_start, stat_ns_wait, stat_ns_tiles, stat_ns_plan;
+  // phases of the (paired or solo) pass as seen by CTA 0 (ns, summed): prologue, tile loop, row finishing, publishing
+  unsigned long long stat_ns_pass[4];
 };
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
@@ -650,9 +652,12 @@ __device__ __forceinline__ ApplyConst apply_const(const PassArgs& a, bool final_
 }
 // tile_mode: 0 streamed, 1 pruned (no dot products were computed: min_d stays), 2 verify (streamed
 // although the filter flagged it: count the rows whose min_d moved anyway — must stay 0)
+// Returns the histogram bin of the row's new score (-1: outside the window / no histogram): the caller adds it
+// warp-aggregated (rows of one track score alike, so per-row shared-memory atomics on one bin — and on the in-window
+// counter — serialised the whole CTA: 145 us of a 1 M-row pass).
 template <int NC = kB>
-__device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c, long long i, const double* s_xxc,
-                                          const long long* s_pick, unsigned int* s_hist, Best& best, int tile_mode = 0) {
+__device__ __forceinline__ int apply_row(const PassArgs& a, const ApplyConst& c, long long i, const double* s_xxc,
+                                         const long long* s_pick, Best& best, int tile_mode = 0) {
   const double2* dp = reinterpret_cast<const double2*>(a.dots + (i - a.lo) * NC);
   const double xxi = a.xx[i];
   double tm = INFINITY;
@@ -681,13 +686,10 @@ __device__ __forceinline__ void apply_row(const PassArgs& a, const ApplyConst& c
     if (c.emit) emit_row(a.send, c.theta_emit, i, dmin, u, sc, best);
     if (c.do_hist) {
       const double fb = (sc - c.h_lo) * c.h_inv;
-      if (fb >= 0.0) {
-        const int hb = (int)fmin(fb, (double)(kNB - 1));
-        atomicAdd(&s_hist[hb], 1u);
-        atomicAdd(&s_hist[kNB], 1u);
-      }
+      if (fb >= 0.0) return (int)fmin(fb, (double)(kNB - 1));
     }
   }
+  return -1;
 }
 
 // ---------------------------------------------------------------- the pass over X, fast path
@@ -780,6 +782,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   }
   const long long* centers = a.centers + a.center_off + kB * crank;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool clocked = !FILTER && a.ctl != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
+  if (clocked) tq0 = gtime_ns();
   const int ncl = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;       // independent tile walkers
   const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   if (!FILTER && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -871,6 +876,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
     }
   }
   __syncthreads();
+  if (clocked) tq1 = gtime_ns();
   const int na = *s_na;
   auto tile_of = [&](int j) -> int { return use_list ? (int)s_tiles[j] : j; };
 
@@ -992,19 +998,46 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   __syncthreads();
   if (FILTER) return;                             // flags written; no rows to finish
   if (PAIR) cluster_sync_all();
+  if (clocked) tq2 = gtime_ns();
   Best best{-INFINITY, 0x7fffffffffffffffLL};
   const ApplyConst ac = apply_const(a, final_pass);
   if (warp < kSeg) {
-    for (int q = threadIdx.x; q < nt * 8; q += kSeg * 32) {
-      const int k = q >> 3;
-      if (PAIR && (k & 1) != crank) continue;
-      const long long i = a.lo + ((long long)cid + (long long)k * ncl) * 8 + (q & 7);
-      const int tile_mode = (use_list && ((s_flagged[k >> 5] >> (k & 31)) & 1u)) ? a.prune_mode : 0;
-      if (i < a.hi) apply_row<NC>(a, ac, i, s_xxc, s_pick, s_hist, best, tile_mode);
+    // this CTA's tiles: every tile of the walker (solo) or the tiles of its parity (pair), rows dealt densely to the
+    // lanes (a warp covers four whole tiles: 128 contiguous bytes of dot products per lane)
+    const int own_tiles = PAIR ? (nt + 1 - crank) / 2 : nt;
+    const int nrows = own_tiles * 8;
+    int inwin = 0;
+    for (int q0 = warp * 32; q0 < nrows; q0 += kSeg * 32) {      // (uniform trip count per warp)
+      const int q = q0 + lane;
+      int bin = -1;
+      if (q < nrows) {
+        const int k = PAIR ? 2 * (q >> 3) + crank : (q >> 3);
+        const long long i = a.lo + ((long long)cid + (long long)k * ncl) * 8 + (q & 7);
+        const int tile_mode = (use_list && ((s_flagged[k >> 5] >> (k & 31)) & 1u)) ? a.prune_mode : 0;
+        if (i < a.hi) bin = apply_row<NC>(a, ac, i, s_xxc, s_pick, best, tile_mode);
+      }
+      if (ac.do_hist) {                                            // one shared atomic per distinct bin per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0) {
+          if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+          inwin += 1;
+        }
+      }
+    }
+    if (ac.do_hist) {
+      inwin = warp_sum(inwin);
+      if (lane == 0 && inwin) atomicAdd(&s_hist[kNB], (unsigned)inwin);
     }
   }
   __syncthreads();
+  if (clocked) tq3 = gtime_ns();
   publish_pass(a, best, ac.do_hist, s_hist, final_pass);
+  if (clocked) {
+    a.ctl->stat_ns_pass[0] += tq1 - tq0;
+    a.ctl->stat_ns_pass[1] += tq2 - tq1;
+    a.ctl->stat_ns_pass[2] += tq3 - tq2;
+    a.ctl->stat_ns_pass[3] += gtime_ns() - tq3;
+  }
 }
 
 // ---------------------------------------------------------------- pruning (exact)
@@ -2415,6 +2448,11 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     host_stats[8] = (int64_t)hc->stat_ns_wait;
     host_stats[9] = (int64_t)hc->stat_ns_tiles;
     host_stats[10] = (int64_t)hc->stat_ns_plan;
+    if (getenv("VATLQ_PASS_PHASES"))
+      fprintf(stderr, "[vatlq] pass phases as seen by CTA 0, us per launch: prologue %.1f, tiles %.1f, finishing %.1f, publish %.1f (%lld launches)\n",
+              hc->stat_ns_pass[0] / 1e3 / std::max<long long>(1, hc->stat_passes), hc->stat_ns_pass[1] / 1e3 / std::max<long long>(1, hc->stat_passes),
+              hc->stat_ns_pass[2] / 1e3 / std::max<long long>(1, hc->stat_passes), hc->stat_ns_pass[3] / 1e3 / std::max<long long>(1, hc->stat_passes),
+              (long long)hc->stat_passes);
     PruneCtl hp{};     // this call's tiles seen / streamed / verify violations / segments (no process-wide state needed)
     if (cudaMemcpy(&hp, P.pc, sizeof(PruneCtl), cudaMemcpyDeviceToHost) == cudaSuccess) {
       host_stats[11] = (int64_t)hp.stats[0];

@@ -285,6 +285,8 @@ def main():
                        "coreset_batch": a.batch,
                        "candidate_exchange": "none" if world == 1 else ("ncclAllGather" if a.no_p2p else "peer-memory mailbox (NVLink stores + flags)"),
                        "coreset_pruning": "off" if a.no_prune else "exact (segments of consecutive rows + triangle inequality; picks unchanged)"})
+    config["arithmetic"] = ("heat-map scores in f32 (THC, peaks, coordinates, WPU MLP), hybrid feature / fusion / distances / selection in f64 "
+                            "(fp64 tensor-core DMMA over the fp32 features); TF32 tcgen05 only as an error-bounded pre-selection")
     config["l2"] = ("inputs (heat maps >= 26 GB and features >= 1 GB per rank) exceed the 126 MB L2" if a.config >= 4 else
                     ("features (819 MB) exceed the 126 MB L2" if a.config == 3 else
                      "L2 flushed between timed iterations (a 256 MB buffer is rewritten)"))
@@ -587,7 +589,7 @@ def full_query(a, n, n_lab, k, moks, config, rank, world, local, dev):
     if rank == 0:
         line = {"metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32 scores / f64 distance accumulation", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "gpu_launches": int(launches),
                 "picks_sha256": digest, "parity": parity,
                 "roofline": roof, "roofline_scan": scan_roof, "e2e": e2e,
@@ -860,7 +862,7 @@ def small_config(a, n, k, moks, config, rank, world, dev):
            "steps": reps, "api": "vatlq.ops operator call with pinned host inputs, results read back"}
     line = {"metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {1: "f32", 2: "f64 feature / f32 MLP", 3: "f64 distance accumulation over f32 features"}[a.config],
+            "dtype": {1: "f32", 2: "f32", 3: "f64"}[a.config],
             "data": "synthetic", "config": config, "clocks": clk.summary(), "gpu_launches": int(launches),
             "roofline": roof, "e2e": e2e, **extra}
     if digest is not None:

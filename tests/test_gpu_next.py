@@ -233,6 +233,47 @@ def test_peak_uncertainties_match_oracle(built_lib, kind):
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), np.abs(got - ref).max()
 
 
+def test_peak_fast_path_equals_generic(built_lib, monkeypatch):
+    """The 64 x 48 register-window path against the generic routine (bit-equal), on smooth maps, noise maps, tied
+    peaks and plateau maps whose candidate list overflows (redone by the generic routine on a list)."""
+    v = built_lib
+    rng = np.random.default_rng(21)
+    n, nj = 300, 17
+    yy, xx = np.mgrid[0:64, 0:48].astype(np.float32)
+    H = np.zeros((n, nj, 64, 48), np.float32)
+    for i in range(n):
+        for j in range(nj):
+            kind = (i * nj + j) % 6
+            if kind == 0:      # a few gaussians (what an estimator emits)
+                for _ in range(int(rng.integers(1, 5))):
+                    cy, cx, a = rng.uniform(0, 64), rng.uniform(0, 48), rng.uniform(0.1, 1.0)
+                    H[i, j] += a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 2.0 ** 2))
+            elif kind == 1:    # noise
+                H[i, j] = rng.normal(0, 0.05, (64, 48))
+            elif kind == 2:    # two-level plateaus: hundreds of pixels equal their window maximum (overflow)
+                H[i, j] = (rng.random((64, 48)) < 0.7).astype(np.float32) * 0.5
+            elif kind == 3:    # quantised: many exact ties
+                H[i, j] = np.round(rng.normal(0, 1, (64, 48)), 0) * 0.25
+            elif kind == 4:    # constant map (trivial image)
+                H[i, j] = rng.uniform(-1, 1)
+            else:              # constant with a single bump on the excluded border and one inside
+                H[i, j, 2, 3] = 1.0
+                H[i, j, 30, 20] = 0.5
+    Hd = torch.from_numpy(H).cuda()
+    fast = v.ops.peak_uncertainty(Hd)
+    monkeypatch.setenv("VATLQ_PEAK_GENERIC", "1")
+    gen = v.ops.peak_uncertainty(Hd)
+    monkeypatch.delenv("VATLQ_PEAK_GENERIC")
+    assert torch.equal(fast[0], gen[0]) and torch.equal(fast[1], gen[1])
+    from oracle import vatl_oracle as O
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_mpe = [O.mpe_item(H[i]) for i in range(12)]
+        ref_mar = [O.margin_item(H[i]) for i in range(12)]
+    assert np.allclose(fast[0][:12].cpu().numpy(), ref_mpe, rtol=1e-5, atol=1e-6)
+    assert np.allclose(fast[1][:12].cpu().numpy(), ref_mar, rtol=1e-5, atol=1e-6)
+
+
 def test_rank_scores_equals_python_stable_sort(built_lib):
     """vatlq_rank_scores reproduces `sorted(dict.items(), key=score, reverse=True)` over a dict in ascending id order
     (ActiveLearning.py:527-530): ties keep ascending ids; negative values, zeros of both signs, infinities."""

@@ -40,6 +40,7 @@ SIGNATURES = {
     "vatlq_cosine_rowsum": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _dbl, _vp, _vp]),
     "vatlq_minmax_stats_f64": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "vatlq_fuse_blend": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
+    "vatlq_peak_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "vatlq_peak_unc": (_int, [_vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "vatlq_rank_workspace_bytes": (_sz, [_i64]),
     "vatlq_rank_scores": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),

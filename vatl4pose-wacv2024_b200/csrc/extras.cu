@@ -86,19 +86,38 @@ __global__ void __launch_bounds__(128) oks_kernel(const float* __restrict__ kpts
 constexpr int kPeakWarps = 4;
 constexpr int kPeakMinDist = 5;
 
+// MPE / Margin of one map from its <= 5 peaks in descending order (one thread)
+__device__ __forceinline__ void peak_scores(const float (&peaks)[5], int npk, float* mpe_out, float* margin_out) {
+  float mpe = 0.f, margin = 0.f;
+  if (npk > 0) {
+    // scipy.special.softmax (fp32): exp(x - max) / sum; scipy.stats.entropy: pk / sum(pk), sum(entr(pk))
+    float e[5], ssum = 0.f;
+    for (int k = 0; k < npk; ++k) {
+      e[k] = expf(peaks[k] - peaks[0]);          // peaks[0] is the maximum (descending order)
+      ssum = __fadd_rn(ssum, e[k]);
+    }
+    float psum = 0.f;
+    for (int k = 0; k < npk; ++k) {
+      e[k] = __fdiv_rn(e[k], ssum);
+      psum = __fadd_rn(psum, e[k]);
+    }
+    for (int k = 0; k < npk; ++k) {
+      const float pk = __fdiv_rn(e[k], psum);
+      mpe = __fadd_rn(mpe, pk > 0.f ? -pk * logf(pk) : 0.f);
+    }
+  }
+  if (npk > 1) margin = fabsf(peaks[0] - peaks[1]);
+  *mpe_out = mpe;
+  *margin_out = margin;
+}
+
 // CH / CW > 0: compile-time map shape (64 x 48: index arithmetic without runtime divisions), else the arguments
 template <int CH, int CW>
-__global__ void __launch_bounds__(kPeakWarps * 32)
-peak_unc_kernel(const float* __restrict__ H, long long maps, int h_, int w_, float* __restrict__ mpe_map,
-                float* __restrict__ margin_map) {
+__device__ __forceinline__ void peak_map_generic(const float* __restrict__ H, long long mi, int h_, int w_, float* __restrict__ mpe_map,
+                                                 float* __restrict__ margin_map, float* img, int lane) {
   const int h = CH > 0 ? CH : h_, w = CW > 0 ? CW : w_;
-  extern __shared__ __align__(16) float s_peak[];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const long long mi = (long long)blockIdx.x * kPeakWarps + wp;
-  if (mi >= maps) return;
   const int npx = h * w;
-  float* img = s_peak + (size_t)wp * 2 * npx;      // the map
-  float* aux = img + npx;                         // row maxima, then the peak mask (as 0 / 1)
+  float* aux = img + npx;                         // row maxima, then the peak mask (as 0 / 1); img: the map
   const float* src = H + (size_t)mi * npx;
   float vmin = INFINITY;
   if (CH > 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -177,29 +196,195 @@ peak_unc_kernel(const float* __restrict__ H, long long maps, int h_, int w_, flo
     }
     __syncwarp();
   }
-  if (lane == 0) {
-    float mpe = 0.f, margin = 0.f;
-    if (npk > 0) {
-      // scipy.special.softmax (fp32): exp(x - max) / sum; scipy.stats.entropy: pk / sum(pk), sum(entr(pk))
-      float e[5], ssum = 0.f;
-      for (int k = 0; k < npk; ++k) {
-        e[k] = expf(peaks[k] - peaks[0]);          // peaks[0] is the maximum (descending order)
-        ssum = __fadd_rn(ssum, e[k]);
-      }
-      float psum = 0.f;
-      for (int k = 0; k < npk; ++k) {
-        e[k] = __fdiv_rn(e[k], ssum);
-        psum = __fadd_rn(psum, e[k]);
-      }
-      for (int k = 0; k < npk; ++k) {
-        const float pk = __fdiv_rn(e[k], psum);
-        mpe = __fadd_rn(mpe, pk > 0.f ? -pk * logf(pk) : 0.f);
+  if (lane == 0) peak_scores(peaks, npk, mpe_map + mi, margin_map + mi);
+}
+
+template <int CH, int CW>
+__global__ void __launch_bounds__(kPeakWarps * 32)
+peak_unc_kernel(const float* __restrict__ H, long long maps, int h_, int w_, float* __restrict__ mpe_map,
+                float* __restrict__ margin_map) {
+  extern __shared__ __align__(16) float s_peak[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long mi = (long long)blockIdx.x * kPeakWarps + wp;
+  if (mi >= maps) return;
+  const int npx = (CH > 0 ? CH : h_) * (CW > 0 ? CW : w_);
+  peak_map_generic<CH, CW>(H, mi, h_, w_, mpe_map, margin_map, s_peak + (size_t)wp * 2 * npx, lane);
+}
+
+// the generic 64 x 48 routine on a list of maps (the fast path's overflow cases); grid-stride over the list
+__global__ void __launch_bounds__(kPeakWarps * 32)
+peak_unc_redo_kernel(const float* __restrict__ H, const unsigned int* __restrict__ redo_count, const int* __restrict__ redo_list,
+                     float* __restrict__ mpe_map, float* __restrict__ margin_map) {
+  extern __shared__ __align__(16) float s_peak[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const unsigned total = *redo_count;
+  for (unsigned slot = blockIdx.x * kPeakWarps + wp; slot < total; slot += gridDim.x * kPeakWarps) {
+    peak_map_generic<64, 48>(H, redo_list[slot], 64, 48, mpe_map, margin_map, s_peak + (size_t)wp * 2 * 64 * 48, lane);
+    __syncwarp();
+  }
+}
+
+
+// ---- 64 x 48 fast path.  The generic kernel above spends ~10 k instructions per lane and map on the two 11-tap
+// window passes (22 shared loads + clamps per pixel) and on five full-map scans for the peaks.  Here:
+//   * the map sits in shared memory with 5 replicated columns on each side (row stride 59: conflict-free when the
+//     lanes walk different rows), the row maxima with 5 replicated rows above and below (row stride 49);
+//   * a lane takes whole rows (then whole columns) into REGISTERS and gets the 11-wide maxima by doubling
+//     (w2 = max(p[i], p[i+1]), w4, w8, out[x] = max(w8[x], w8[x+3])): 4 max ops per element, no clamps;
+//   * mask pixels (a few dozen per map) are appended to a candidate list; the five rounds of "best remaining
+//     peak + Chebyshev-< 5 suppression" run on the list.  A list overflow (large plateaus) is flagged and the map
+//     is redone by the generic kernel.
+constexpr int kPfW = 48, kPfH = 64, kPfPad = kPeakMinDist;
+constexpr int kPfPS = kPfW + 2 * kPfPad + 1;            // 59: padded image row stride
+constexpr int kPfRS = kPfW + 1;                         // 49: row-maxima row stride
+constexpr int kPfRows = kPfH + 2 * kPfPad;              // 74 rows of row maxima
+constexpr int kPfCand = 256;
+constexpr int kPfWarps = 7;
+constexpr size_t kPfSmemWarp = (size_t)(kPfH * kPfPS + kPfRows * kPfRS) * 4 + kPfCand * 8 + 16;
+
+template <int N>
+__device__ __forceinline__ void window11(float (&p)[N]) {   // p[i] <- max(p[i .. i+10]) for i < N - 10, in place
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) p[i] = fmaxf(p[i], p[i + 1]);      // width 2
+#pragma unroll
+  for (int i = 0; i < N - 3; ++i) p[i] = fmaxf(p[i], p[i + 2]);      // width 4
+#pragma unroll
+  for (int i = 0; i < N - 7; ++i) p[i] = fmaxf(p[i], p[i + 4]);      // width 8
+#pragma unroll
+  for (int i = 0; i < N - 10; ++i) p[i] = fmaxf(p[i], p[i + 3]);     // width 11
+}
+
+__global__ void __launch_bounds__(kPfWarps * 32, 1)
+peak_unc_fast_kernel(const float* __restrict__ H, long long maps, float* __restrict__ mpe_map, float* __restrict__ margin_map,
+                     unsigned int* __restrict__ redo_count, int* __restrict__ redo_list) {
+  extern __shared__ __align__(16) unsigned char pf_smem[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long mi = (long long)blockIdx.x * kPfWarps + wp;
+  if (mi >= maps) return;
+  float* P = reinterpret_cast<float*>(pf_smem + (size_t)wp * kPfSmemWarp);     // [64][59]
+  float* R = P + kPfH * kPfPS;                                                  // [74][49]
+  float* cval = R + kPfRows * kPfRS;                                            // [256]
+  int* cidx = reinterpret_cast<int*>(cval + kPfCand);                           // [256]
+  int* ccount = cidx + kPfCand;
+  const float4* src = reinterpret_cast<const float4*>(H + (size_t)mi * (kPfH * kPfW));
+  float vmin = INFINITY;
+  if (lane == 0) *ccount = 0;
+#pragma unroll 4
+  for (int i = lane; i < kPfH * kPfW / 4; i += 32) {       // 12 float4 per row
+    const float4 v = ldg_stream(src + i);
+    const int y = i / 12, x = (i - y * 12) * 4;
+    float* d = P + y * kPfPS + kPfPad + x;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+  __syncwarp();
+  // row pass: lane takes rows lane and lane + 32 into registers (edge columns replicated)
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int y = lane + 32 * rr;
+    float p[kPfW + 2 * kPfPad];
+    const float* row = P + y * kPfPS;
+#pragma unroll
+    for (int i = 0; i < kPfW; ++i) p[kPfPad + i] = row[kPfPad + i];
+#pragma unroll
+    for (int i = 0; i < kPfPad; ++i) {
+      p[i] = p[kPfPad];
+      p[kPfPad + kPfW + i] = p[kPfPad + kPfW - 1];
+    }
+    window11(p);
+    float* out = R + (y + kPfPad) * kPfRS;
+#pragma unroll
+    for (int x = 0; x < kPfW; ++x) out[x] = p[x];
+    if (y == 0) {
+#pragma unroll 1
+      for (int e = 0; e < kPfPad; ++e)
+#pragma unroll
+        for (int x = 0; x < kPfW; ++x) R[e * kPfRS + x] = p[x];
+    }
+    if (y == kPfH - 1) {
+#pragma unroll 1
+      for (int e = 0; e < kPfPad; ++e)
+#pragma unroll
+        for (int x = 0; x < kPfW; ++x) R[(kPfH + kPfPad + e) * kPfRS + x] = p[x];
+    }
+  }
+  __syncwarp();
+  // column pass: lane takes columns lane and lane + 32 (< 48); mask and candidates
+  int n_eq = 0;
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    const int x = lane + 32 * cc;
+    if (x < kPfW) {
+      float c[kPfRows];
+#pragma unroll
+      for (int i = 0; i < kPfRows; ++i) c[i] = R[i * kPfRS + x];
+      window11(c);
+      const bool xin = x >= kPfPad && x < kPfW - kPfPad;
+#pragma unroll
+      for (int y = 0; y < kPfH; ++y) {
+        const float v = P[y * kPfPS + kPfPad + x];
+        const bool eq = v == c[y];
+        n_eq += eq ? 1 : 0;
+        if (eq && xin && y >= kPfPad && y < kPfH - kPfPad && v > vmin) {
+          const int pos = atomicAdd(ccount, 1);
+          if (pos < kPfCand) {
+            cval[pos] = v;
+            cidx[pos] = y * kPfW + x;
+          }
+        }
       }
     }
-    if (npk > 1) margin = fabsf(peaks[0] - peaks[1]);
-    mpe_map[mi] = mpe;
-    margin_map[mi] = margin;
   }
+  n_eq = warp_sum(n_eq);
+  __syncwarp();
+  int ncand = *ccount;
+  if (n_eq == kPfH * kPfW) ncand = 0;                       // trivial image: no peak at all
+  if (ncand > kPfCand) {                                     // large plateaus: the generic kernel redoes this map
+    if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int)mi;
+    return;
+  }
+  // candidates lane + 32 j in registers
+  float v8[kPfCand / 32];
+  int i8[kPfCand / 32];
+#pragma unroll
+  for (int j = 0; j < kPfCand / 32; ++j) {
+    const int q = lane + 32 * j;
+    v8[j] = q < ncand ? cval[q] : -INFINITY;
+    i8[j] = q < ncand ? cidx[q] : 0x7fffffff;
+  }
+  float peaks[5];
+  int npk = 0;
+  for (int r = 0; r < 5; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kPfCand / 32; ++j)
+      if (i8[j] != 0x7fffffff && (v8[j] > bv || (v8[j] == bv && i8[j] < bi))) {
+        bv = v8[j];
+        bi = i8[j];
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (i2 != 0x7fffffff && (bi == 0x7fffffff || v2 > bv || (v2 == bv && i2 < bi))) {
+        bv = v2;
+        bi = i2;
+      }
+    }
+    if (bi == 0x7fffffff) break;
+    peaks[npk++] = bv;
+    const int py = bi / kPfW, px = bi - py * kPfW;
+#pragma unroll
+    for (int j = 0; j < kPfCand / 32; ++j)
+      if (i8[j] != 0x7fffffff) {
+        const int yy = i8[j] / kPfW, xx = i8[j] - yy * kPfW;
+        if (abs(yy - py) < kPeakMinDist && abs(xx - px) < kPeakMinDist) i8[j] = 0x7fffffff;
+      }
+  }
+  if (lane == 0) peak_scores(peaks, npk, mpe_map + mi, margin_map + mi);
 }
 
 // per-frame sums over the joints, in joint order
@@ -323,6 +508,13 @@ extern "C" int vatlq_rank_scores(const double* score, const uint8_t* mask, int64
   return 0;
 }
 
+extern "C" size_t vatlq_peak_workspace_bytes(int64_t n, int J, int h, int w) {
+  if (n <= 0 || J <= 0) return 0;
+  const size_t maps = (size_t)n * J;
+  // two floats per map; the 64 x 48 fast path adds its overflow list (a counter + one int per map)
+  return maps * 8 + ((h == kPfH && w == kPfW) ? 16 + maps * 4 : 0);
+}
+
 extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, float* mpe, float* margin, void* ws,
                               size_t ws_bytes, vatlq_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -331,20 +523,38 @@ extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, fl
   VQ_REQUIRE(H && ws && (mpe || margin), "null pointer");
   VQ_REQUIRE(h * w <= 128 * 32 * 4, "map too large (<= 16384 pixels)");
   const long long maps = (long long)n * J;
-  VQ_REQUIRE(ws_bytes >= (size_t)maps * 8, "workspace must hold 2 floats per map");
+  VQ_REQUIRE(maps < (1LL << 31), "too many maps per call (n*J < 2^31)");
+  VQ_REQUIRE(ws_bytes >= vatlq_peak_workspace_bytes(n, J, h, w), "workspace too small (vatlq_peak_workspace_bytes)");
   const size_t smem = (size_t)kPeakWarps * 2 * h * w * sizeof(float);
   VQ_REQUIRE(smem <= 200 * 1024, "map too large for the shared-memory staging");
   static size_t configured = 0;
   if (smem > configured) {
     VQ_CUDA(cudaFuncSetAttribute((peak_unc_kernel<0, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQ_CUDA(cudaFuncSetAttribute((peak_unc_kernel<64, 48>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQ_CUDA(cudaFuncSetAttribute(peak_unc_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)kPeakWarps * 2 * kPfH * kPfW * sizeof(float))));
+    VQ_CUDA(cudaFuncSetAttribute(peak_unc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPfWarps * kPfSmemWarp)));
     configured = smem;
   }
   float* mm = (float*)ws;
-  const unsigned pgrid = (unsigned)((maps + kPeakWarps - 1) / kPeakWarps);
-  if (h == 64 && w == 48) peak_unc_kernel<64, 48><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
-  else peak_unc_kernel<0, 0><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
-  VQ_LAUNCHED();
+  const bool no_fast = getenv("VATLQ_PEAK_GENERIC") != nullptr;     // measurement / test switch (read per call)
+  if (h == kPfH && w == kPfW && !no_fast && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+    unsigned int* redo_count = (unsigned int*)((char*)ws + (size_t)maps * 8);
+    int* redo_list = (int*)((char*)ws + (size_t)maps * 8 + 16);
+    VQ_CUDA(cudaMemsetAsync(redo_count, 0, 16, stream));
+    peak_unc_fast_kernel<<<(unsigned)((maps + kPfWarps - 1) / kPfWarps), kPfWarps * 32, kPfWarps * kPfSmemWarp, stream>>>(
+        H, maps, mm, mm + maps, redo_count, redo_list);
+    VQ_LAUNCHED();
+    const unsigned rgrid = (unsigned)std::min<long long>((maps + kPeakWarps - 1) / kPeakWarps, (long long)sm_count() * 4);
+    peak_unc_redo_kernel<<<rgrid, kPeakWarps * 32, (size_t)kPeakWarps * 2 * kPfH * kPfW * sizeof(float), stream>>>(
+        H, redo_count, redo_list, mm, mm + maps);
+    VQ_LAUNCHED();
+  } else {
+    const unsigned pgrid = (unsigned)((maps + kPeakWarps - 1) / kPeakWarps);
+    if (h == 64 && w == 48) peak_unc_kernel<64, 48><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
+    else peak_unc_kernel<0, 0><<<pgrid, kPeakWarps * 32, smem, stream>>>(H, maps, h, w, mm, mm + maps);
+    VQ_LAUNCHED();
+  }
   peak_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mm, mm + maps, (long long)n, J, mpe, margin);
   VQ_LAUNCHED();
   return 0;

@@ -452,9 +452,9 @@ def peak_uncertainty(H: torch.Tensor, want_mpe: bool = True, want_margin: bool =
     n, nj, h, w = H.shape
     mpe = torch.empty(n, dtype=torch.float32, device=H.device) if want_mpe else None
     mar = torch.empty(n, dtype=torch.float32, device=H.device) if want_margin else None
-    ws = torch.empty(max(n * nj * 2, 1), dtype=torch.float32, device=H.device)
+    ws = torch.empty(max(int(_lib.lib().vatlq_peak_workspace_bytes(n, nj, h, w)), 16), dtype=torch.uint8, device=H.device)
     with torch.cuda.device(H.device):
-        _lib.check(_lib.lib().vatlq_peak_unc(_ptr(H), n, nj, h, w, _ptr(mpe), _ptr(mar), _ptr(ws), ws.numel() * 4, _stream()),
+        _lib.check(_lib.lib().vatlq_peak_unc(_ptr(H), n, nj, h, w, _ptr(mpe), _ptr(mar), _ptr(ws), ws.numel(), _stream()),
                    "vatlq_peak_unc")
     return mpe, mar
 

@@ -256,6 +256,59 @@ int vatlq_rank_scores(const double* score, const uint8_t* mask, int64_t n, int d
 int vatlq_oks(const float* kpts, const float* gt_kpts, const float* bbox_ann_xyxy, int64_t n, double* oks,
               vatlq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * K-Means / weighted K-Means query filters (ActiveLearning.py:593-608 and :553-580): the device side of
+ * sklearn.cluster.KMeans(n_clusters=query_size, random_state=318).fit_predict(embeddings[, sample_weight]) followed
+ * by "per cluster, the member closest to its centre".  sklearn's algorithm (1.7.1 pinned by the reference:
+ * _kmeans.py _kmeans_plusplus / _kmeans_single_lloyd, _k_means_lloyd.pyx, _k_means_common.pyx) in fp64 over the
+ * fp32 embeddings; both GEMM-shaped steps run on the fp64 tensor cores.  The host layer (kmeans.py) draws the random
+ * numbers from numpy's RandomState exactly as sklearn does and decides convergence from a few scalars.
+ * X (n,d) fp32 row-major, 16-byte aligned, d % 4 == 0, n < 2^31; w fp64[n] sample weights or NULL (all 1).
+ * One workspace of vatlq_kmeans_workspace_bytes(n,d,k) serves every call (they never overlap).
+ *
+ * Which bits matter: label decisions are robust to rounding, but the closest member of a TWO-member cluster is a
+ * structural tie that the reference resolves by the rounding of its own arithmetic; the M step and the final
+ * distances therefore follow sklearn / numpy operation by operation in the centred frame (see csrc/kmeans.cu).
+ *
+ * _mean_var   mean[d] = X.mean(axis=0) (numpy's sequential order), out1[0] = np.mean(np.var(X, axis=0)) (_tolerance)
+ * _pp         k-means++ seeding: center_ids[k] (row ids), closest[n] = squared distance to the nearest seed.
+ *             first_center = random_state.choice(n, p=w/sum(w)); rand_vals[(k-1)*trials] = the uniform draws of the
+ *             k-1 later steps in order, trials = 2 + int(log(k)) <= 16.  No host synchronisation inside.
+ * _gather     Cc[k][d] = X[ids[j]] - mean (centred frame, where sklearn keeps its centres), Cr = Cc + mean
+ * _assign     labels[i] = first argmin_j (|c_j|^2 - 2 x_i.c_j) over the raw-frame centres C; *changed = #rows with
+ *             labels[i] != labels_old[i] (labels_old / changed may be NULL)
+ * _update     M step: order[n] = rows sorted by (label, row), starts[k+1], sums[k][d] = sum (x_i - mean) w_i in
+ *             ascending row order, wsum[k], *n_empty = #clusters with zero weight
+ * _relocate   _relocate_empty_clusters_dense for the (empty cluster, far row) pairs the host chose
+ * _average    Cc_new = sums * (1 / wsum) (argmax_weight >= 0: clusters that stayed empty copy that cluster's row the
+ *             way _average_centers does), Cr_new = Cc_new + mean, shift[j] = |Cc_new[j] - Cc_old[j]|
+ * _rowdist    dis[i] = ((x_i - C[labels[i]]) ** 2).sum() in numpy's pairwise summation order     (:601-602)
+ * _pick       picks[j] = member of cluster j with the smallest dis, lowest row on ties; -1 for an empty cluster (:603)
+ * ------------------------------------------------------------------------------------ */
+size_t vatlq_kmeans_workspace_bytes(int64_t n, int d, int64_t k);
+int vatlq_kmeans_mean_var(const float* X, int64_t n, int d, double* mean, double* out1, void* ws, size_t ws_bytes,
+                          vatlq_stream_t stream);
+int vatlq_kmeans_pp(const float* X, int64_t n, int d, const double* w, int64_t k, int64_t first_center,
+                    const double* rand_vals, int trials, int32_t* center_ids, double* closest, void* ws, size_t ws_bytes,
+                    vatlq_stream_t stream);
+int vatlq_kmeans_gather(const float* X, int d, const int32_t* ids, int64_t k, const double* mean, double* Cc, double* Cr,
+                        vatlq_stream_t stream);
+int vatlq_kmeans_assign(const float* X, int64_t n, int d, const double* C, int64_t k, int32_t* labels,
+                        const int32_t* labels_old, int32_t* changed, void* ws, size_t ws_bytes, vatlq_stream_t stream);
+int vatlq_kmeans_update(const float* X, int64_t n, int d, const double* w, const double* mean, const int32_t* labels,
+                        int64_t k, double* sums, double* wsum, int32_t* order, int32_t* starts, int32_t* n_empty, void* ws,
+                        size_t ws_bytes, vatlq_stream_t stream);
+int vatlq_kmeans_relocate(const float* X, int d, const double* w, const double* mean, const int32_t* labels,
+                          const int32_t* empty_ids, const int32_t* far_ids, int n_empty, double* sums, double* wsum,
+                          vatlq_stream_t stream);
+int vatlq_kmeans_average(const double* sums, const double* wsum, int64_t k, int d, int64_t argmax_weight,
+                         const double* mean, const double* Cc_old, double* Cc_new, double* Cr_new, double* shift,
+                         vatlq_stream_t stream);
+int vatlq_kmeans_rowdist(const float* X, int64_t n, int d, const double* C, const int32_t* labels, double* dis,
+                         vatlq_stream_t stream);
+int vatlq_kmeans_pick(const double* dis, const int32_t* order, const int32_t* starts, int64_t k, int32_t* picks,
+                      vatlq_stream_t stream);
+
 /* fp64 tensor-core (mma.sync.m8n8k4.f64, DMMA) peak of the current device in FMA/s, measured with a saturating
  * register-only kernel (about 10 ms): the roofline denominator of the paired core-set pass, which is bound by the
  * DMMA pipe rather than by HBM.  ws >= 4 * SMs * 256 * 8 bytes. */

@@ -248,7 +248,86 @@ def pin_peaks(R, O, synth):
     print("MPE / Margin pinned (peak_local_max restated):", mpe[:3], mar[:3])
 
 
+def _reference_branch(src_lines, head):
+    """The statements of one `elif self.filter==...:` branch of eval_and_query, de-indented, as a code object."""
+    import textwrap
+    start = next(i for i, l in enumerate(src_lines) if l.strip().startswith(head))
+    ind = len(src_lines[start]) - len(src_lines[start].lstrip())
+    body = []
+    for l in src_lines[start + 1:]:
+        if l.strip() and (len(l) - len(l.lstrip())) <= ind:
+            break
+        body.append(l)
+    return compile(textwrap.dedent("".join(body)), f"<reference {head}>", "exec")
+
+
+def kmeans_cases(synth):
+    """(tag, X fp32 (n,2048), candidate_list, total_score over the candidates, query_size, w_unc, combine_weight)."""
+    out = []
+    for tag, kind, n, n_lab, k, seed in (("clustered", "clustered", 600, 60, 27, 2), ("weak", "weak", 900, 0, 45, 4),
+                                         ("iid", "iid", 500, 100, 20, 5), ("pairs", "iid", 240, 0, 150, 6),
+                                         ("one", "clustered", 200, 0, 1, 7), ("all", "weak", 64, 0, 64, 8)):
+        X = synth.pool_embeddings(n, kind=kind, seed=seed)
+        lab = set(synth.pool_labeled(n, n_lab, seed=seed).tolist())
+        cand = [i for i in range(n) if i not in lab]
+        score = synth.pool_unc(n, seed=seed)[cand]
+        out.append((tag, dict(kind=kind, n=n, n_lab=n_lab, seed=seed, dup=np.zeros(0, np.int64)), X, cand, score, k, 0.7, 0.35))
+    # duplicated rows (np.unique has work to do; two-member clusters of identical rows)
+    n, seed = 400, 9
+    X = synth.pool_embeddings(n, kind="iid", seed=seed)
+    dup = np.arange(100, 160)
+    X[dup] = X[dup - 100]
+    cand = list(range(n))
+    out.append(("dups", dict(kind="iid", n=n, n_lab=0, seed=seed, dup=dup), X, cand, synth.pool_unc(n, seed=seed), 120, 1.3, 0.5))
+    return out
+
+
+def pin_kmeans(R, O, synth):
+    """K-Means / weighted filters: the reference's OWN statements (ActiveLearning.py:553-580 and :593-608, taken
+    from the source file and executed here) against the oracle restatement; sklearn is the same library call in
+    both.  Golden: pool parameters (the pools are counter-based), labels and query lists."""
+    from sklearn.cluster import KMeans
+    with open(os.path.join(REF, "active_learning", "ActiveLearning.py")) as fh:
+        src = fh.readlines()
+    code = {"K-Means": _reference_branch(src, 'elif self.filter=="K-Means":'),
+            "weighted": _reference_branch(src, 'elif self.filter=="weighted":')}
+    gold = {}
+    for tag, meta, X, cand, score, k, w_unc, cw in kmeans_cases(synth):
+        fvecs = X.astype(np.float64)                           # fvecs_matrix is float64 (:270)
+        for filt in ("K-Means", "weighted"):
+            me = SimpleNamespace(unlabeled_id=SimpleNamespace(index=list(cand)), query_size=k, plot_cluster=False, w_unc=w_unc)
+            env = dict(np=np, KMeans=KMeans, self=me, fvecs_matrix=fvecs, candidate_list=list(cand),
+                       track_ids_list=np.zeros(len(fvecs)), total_score=score.copy(), combine_weight=cw)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                exec(code[filt], env)
+                if filt == "K-Means":
+                    q, qs, lab = O.kmeans_filter(fvecs, cand, k)
+                    eidx = np.zeros(0, np.int64)
+                else:
+                    q, qs, lab, eidx = O.weighted_kmeans_filter(fvecs, cand, score, w_unc, cw, k)
+            assert env["query_list"] == q, (tag, filt)
+            assert me.query_size == qs, (tag, filt)
+            same(env["cluster_idxs"], lab, f"kmeans labels {tag} {filt}")
+            key = f"{tag}_{'km' if filt == 'K-Means' else 'wk'}"
+            gold[key + "_query"] = np.asarray(q, np.int64)
+            gold[key + "_labels"] = np.asarray(lab, np.int32)
+            gold[key + "_embed_idx"] = np.asarray(eidx, np.int64)
+            gold[key + "_qsize"] = np.int64(qs)
+            gold[key + "_niter"] = np.int64(env["cluster_learner"].n_iter_)
+        gold[tag + "_meta"] = np.array([meta["n"], meta["n_lab"], meta["seed"], k], np.int64)
+        gold[tag + "_kind"] = np.array(meta["kind"])
+        gold[tag + "_dup"] = meta["dup"]
+        gold[tag + "_w"] = np.array([w_unc, cw])
+        print("K-Means / weighted pinned:", tag, len(gold[tag + "_km_query"]), len(gold[tag + "_wk_query"]))
+    np.savez_compressed(os.path.join(GOLD, "kmeans.npz"), **gold)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "kmeans":
+        from oracle import vatl_oracle as O
+        pin_kmeans(import_reference(), O, importlib.import_module("vatl4pose-wacv2024_b200.synth"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "peaks":
         from oracle import vatl_oracle as O
         pin_peaks(import_reference(), O, importlib.import_module("vatl4pose-wacv2024_b200.synth"))
@@ -406,6 +485,7 @@ def main():
     pin_next_rows(R, O, synth)
     pin_oks(R, O, synth)
     pin_peaks(R, O, synth)
+    pin_kmeans(R, O, synth)
     print("oracle pinned against the reference; fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(f"  {fn}: {os.path.getsize(os.path.join(GOLD, fn)) / 1e6:.2f} MB")

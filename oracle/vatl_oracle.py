@@ -558,3 +558,51 @@ def score_pool(H, boxes_xyxy, is_prev, is_next, ae, unlabeled_mask=None, drop_ea
         if "peak" in want and (unlabeled_mask is None or unlabeled_mask[i]):
             out["peak"][i] = localpeak_mean(H[i])
     return out
+
+
+# --------------------------------------------------------------------------------------
+# K-Means / weighted K-Means filters (ActiveLearning.py:593-608, :553-580).  The clustering itself is the
+# third-party dependency the reference calls (scikit-learn, 1.7.1 pinned by the reference, 1.9.0 here): the oracle
+# calls it too; the lines around it are restated.  pin_against_reference.py executes the reference's own source
+# lines of both branches and compares.
+# --------------------------------------------------------------------------------------
+def _closest_member_per_cluster(embeddings, cluster_learner, cluster_idxs):
+    cluster_num = len(np.unique(cluster_idxs))                                         # (:571,598)
+    centers = cluster_learner.cluster_centers_[cluster_idxs]                           # (:572,599)
+    dis = ((embeddings - centers) ** 2).sum(axis=1)                                    # (:573-574,600-601)
+    return [int(np.arange(embeddings.shape[0])[cluster_idxs == i][dis[cluster_idxs == i].argmin()])
+            for i in range(cluster_num)]                                               # (:575,602)
+
+
+def kmeans_filter(fvecs_matrix, candidate_list, query_size, n_unlabeled=None):
+    """filter == "K-Means" (:593-608): returns (query_list, query_size, labels)."""
+    from sklearn.cluster import KMeans
+    embeddings = np.asarray(fvecs_matrix, dtype=np.float64)[candidate_list]
+    n_unlabeled = len(candidate_list) if n_unlabeled is None else n_unlabeled
+    if n_unlabeled < query_size:
+        query_size = n_unlabeled
+    cluster_learner = KMeans(n_clusters=query_size, random_state=318)
+    cluster_idxs = cluster_learner.fit_predict(embeddings)
+    rows = _closest_member_per_cluster(embeddings, cluster_learner, cluster_idxs)
+    return [int(candidate_list[i]) for i in rows], query_size, cluster_idxs
+
+
+def weighted_kmeans_filter(fvecs_matrix, candidate_list, total_score, w_unc, combine_weight, query_size, n_unlabeled=None):
+    """filter == "weighted" (:553-580): duplicates removed with np.unique(axis=0) (which also SORTS the rows), weights
+    1 + w_unc * combine_weight * total_score; the reference maps the chosen rows of the de-duplicated, sorted matrix
+    straight through candidate_list (:580) — kept as it is.  Returns (query_list, query_size, labels, embed_idx)."""
+    from sklearn.cluster import KMeans
+    embeddings = np.asarray(fvecs_matrix, dtype=np.float64)[candidate_list]
+    _, embed_idx = np.unique(embeddings, axis=0, return_index=True)
+    embeddings = embeddings[embed_idx]
+    weight = 1 + w_unc * combine_weight * np.asarray(total_score, dtype=np.float64)
+    weight = weight[embed_idx]
+    n_unlabeled = len(candidate_list) if n_unlabeled is None else n_unlabeled
+    if n_unlabeled <= query_size:
+        query_size = n_unlabeled
+    if query_size > len(embeddings):
+        query_size = len(embeddings)
+    cluster_learner = KMeans(n_clusters=query_size, random_state=318, verbose=0)
+    cluster_idxs = cluster_learner.fit_predict(embeddings, sample_weight=weight)
+    rows = _closest_member_per_cluster(embeddings, cluster_learner, cluster_idxs)
+    return [int(candidate_list[i]) for i in rows], query_size, cluster_idxs, embed_idx

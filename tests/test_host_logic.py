@@ -103,10 +103,8 @@ def test_strategy_names_and_errors():
         al = ActiveLearning(*_cfg_opt(u), eval_len=10)
         with pytest.raises(NotImplementedError):
             al._require_accelerated()
-    for f in ("weighted", "K-Means"):
-        al = ActiveLearning(*_cfg_opt("THC", "None", f), eval_len=10)
-        with pytest.raises(NotImplementedError):
-            al._require_accelerated()
+    for f in ("weighted", "K-Means"):       # device K-Means filters (kmeans.py / csrc/kmeans.cu)
+        ActiveLearning(*_cfg_opt("THC", "None", f), eval_len=10)._require_accelerated()
     for u in ("THC", "THC_L1", "WPU", "WPU_hybrid", "THC+WPU", "None", "HP", "TPC", "Entropy", "MPE", "Margin"):
         ActiveLearning(*_cfg_opt(u), eval_len=10)._require_accelerated()
     for r, f in (("Influence", "None"), ("Random", "Diversity"), ("None", "Random"), ("Influence", "Coreset")):

@@ -44,6 +44,16 @@ SIGNATURES = {
     "vatlq_peak_unc": (_int, [_vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "vatlq_rank_workspace_bytes": (_sz, [_i64]),
     "vatlq_rank_scores": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "vatlq_kmeans_workspace_bytes": (_sz, [_i64, _int, _i64]),
+    "vatlq_kmeans_mean_var": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "vatlq_kmeans_pp": (_int, [_vp, _i64, _int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
+    "vatlq_kmeans_gather": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "vatlq_kmeans_assign": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vatlq_kmeans_update": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vatlq_kmeans_relocate": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "vatlq_kmeans_average": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vatlq_kmeans_rowdist": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "vatlq_kmeans_pick": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "vatlq_measure_fp64_mma": (_int, [_vp, _vp, _sz, _vp]),
     "vatlq_oks": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "vatlq_profile_passes": (_int, [_int]),

@@ -310,8 +310,6 @@ class ActiveLearning:
             raise NotImplementedError(
                 f"uncertainty '{u}' is not on the accelerated path: run the reference's "
                 "ActiveLearning.eval_and_query (active_learning/ActiveLearning.py:329-401) for it")
-        if self.filter not in ("None", "Coreset", "Diversity", "Random"):
-            raise NotImplementedError("filter '%s': use the reference (ActiveLearning.py:553-608)" % self.filter)
 
     @torch.no_grad()
     def eval_and_query(self):
@@ -450,6 +448,8 @@ class ActiveLearning:
                 q = int(np.random.choice(cand))
                 query_list.append(q)
                 cand.remove(q)
+        elif self.filter in ("K-Means", "weighted"):                                   # (:553-580, 593-608)
+            query_list = self._kmeans_query(X, score, unl_idx, qp.combine_weight)
         else:                                                                          # Coreset (:609-614)
             holder = SimpleNamespace(labeled_id=self.labeled_id, moks_queried=self.moks_queried,
                                      unc_lambda=self.unc_lambda, uncertainty=self.uncertainty, cfg=self.cfg,
@@ -491,6 +491,35 @@ class ActiveLearning:
                 if self.actual_finish < 100:
                     self.is_early_stop = True                                          # (:646-649)
         return None
+
+    def _kmeans_query(self, X, score, unl_idx, combine_weight):
+        """filter == "K-Means" (:593-608) / "weighted" (:553-580): sklearn's KMeans(n_clusters=query_size,
+        random_state=318) on the embeddings of every unlabelled item, restated on the device (kmeans.py), then per
+        cluster the member closest to its centre.  `weighted` first drops duplicate embeddings with
+        np.unique(axis=0) — which also sorts the rows — weighs every row with 1 + w_unc * combine_weight * score, and
+        maps the chosen rows of that sorted matrix straight through candidate_list (:580, kept as the reference has
+        it).  self.query_size is clamped in place like the reference does."""
+        from . import kmeans as KM
+        dev = X.device
+        cand = sorted(int(i) for i in unl_idx)                                        # (:535-536)
+        cand_t = torch.as_tensor(cand, dtype=torch.int64, device=dev)
+        emb = X[cand_t]
+        if self.filter == "weighted":
+            embed_idx = KM.unique_rows_first_index(emb)                                # (:555-556)
+            e_t = torch.as_tensor(embed_idx, dtype=torch.int64, device=dev)
+            emb = emb[e_t]
+            weight = (1 + self.w_unc * combine_weight * score[cand_t])[e_t].contiguous()   # (:560-562)
+            if len(unl_idx) <= self.query_size:
+                self.query_size = len(unl_idx)
+            if self.query_size > emb.shape[0]:
+                self.query_size = int(emb.shape[0])
+            res = KM.kmeans_fit_select(emb, self.query_size, sample_weight=weight)
+        else:
+            if len(unl_idx) < self.query_size:
+                self.query_size = len(unl_idx)
+            res = KM.kmeans_fit_select(emb, self.query_size)
+        self.kmeans_stats = {"n_iter": res.n_iter, "relocations": res.relocations}
+        return [int(cand[i]) for i in res.query_rows]
 
     # ---- host bookkeeping on the per-item OKS values (tiny; ActiveLearning.py:707-725, 852-884) ----
     def get_retrain_id(self, query_list, OKS_dict):

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvatlq.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "heatmap_scan.cu", "wpu.cu", "fuse.cu", "coreset.cu", "next_rows.cu", "extras.cu", "tc_dist.cu"]
+SOURCES = ["api.cu", "heatmap_scan.cu", "wpu.cu", "fuse.cu", "coreset.cu", "next_rows.cu", "extras.cu", "tc_dist.cu", "kmeans.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

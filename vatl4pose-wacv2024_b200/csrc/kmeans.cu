@@ -280,116 +280,121 @@ struct PpState {
 
 constexpr int kPotBlocks = 512;
 
-// partial potentials: part[b][t] = sum over the block's rows of w_i * min(closest_i, D[i][t]), fixed order
+// partial potentials: part[b][t] = sum over the block's rows of w_i * min(closest_i, D[i][t]), fixed order.
+// BN = row stride of D = candidates computed per row (8 or 16)
+template <int BN>
 __global__ void __launch_bounds__(256) km_pot_partial_kernel(const double* __restrict__ D, const double* __restrict__ closest,
-                                                             const double* __restrict__ w, long long n, int trials,
-                                                             double* __restrict__ part) {
-  __shared__ double s_p[8][16];
+                                                             const double* __restrict__ w, long long n, double* __restrict__ part) {
+  __shared__ double s_p[8][BN];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double p[16];
+  double p[BN];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) p[t] = 0.0;
+  for (int t = 0; t < BN; ++t) p[t] = 0.0;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(n, lo + per);
   for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const double c = closest[i], wi = w ? w[i] : 1.0;
-    const double2* dr = reinterpret_cast<const double2*>(D + (size_t)i * 16);
+    const double2* dr = reinterpret_cast<const double2*>(D + (size_t)i * BN);
 #pragma unroll
-    for (int t2 = 0; t2 < 8; ++t2) {
+    for (int t2 = 0; t2 < BN / 2; ++t2) {
       const double2 v = dr[t2];
       p[2 * t2] = __dadd_rn(p[2 * t2], __dmul_rn(wi, fmin(c, v.x)));
       p[2 * t2 + 1] = __dadd_rn(p[2 * t2 + 1], __dmul_rn(wi, fmin(c, v.y)));
     }
   }
 #pragma unroll
-  for (int t = 0; t < 16; ++t) {
+  for (int t = 0; t < BN; ++t) {
     p[t] = warp_sum(p[t]);
     if (lane == 0) s_p[warp][t] = p[t];
   }
   __syncthreads();
-  if (threadIdx.x < 16) {
+  if (threadIdx.x < BN) {
     double s = 0.0;
     for (int w2 = 0; w2 < 8; ++w2) s = __dadd_rn(s, s_p[w2][threadIdx.x]);
     part[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
   }
-  (void)trials;
 }
 
-// potentials of the candidates (fixed-order sum of the partials), best = first minimum among the live ones
-__global__ void __launch_bounds__(32) km_pot_final_kernel(const double* __restrict__ part, int blocks, int trials, PpState* st,
-                                                          int* __restrict__ center_ids, int step) {
-  const int t = threadIdx.x;
+// potentials of the candidates (warp t sums the partials of candidate t in a fixed order), best = first minimum
+__global__ void __launch_bounds__(512) km_pot_final_kernel(const double* __restrict__ part, int blocks, int trials, PpState* st,
+                                                           int* __restrict__ center_ids, int step) {
+  __shared__ double s_pot[16];
+  const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0.0;
-  if (t < 16)
-    for (int b = 0; b < blocks; ++b) s = __dadd_rn(s, part[(size_t)b * 16 + t]);
-  double bv = (t < trials) ? s : INFINITY;
-  int bt = (t < trials) ? t : 0x7fffffff;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-    if (t2 != 0x7fffffff && (bt == 0x7fffffff || v2 < bv || (v2 == bv && t2 < bt))) {
-      bv = v2;
-      bt = t2;
-    }
-  }
-  if (t < 16) st->pot[t] = s;
-  if (t == 0) {
+  if (t < trials)
+    for (int b = lane; b < blocks; b += 32) s = __dadd_rn(s, part[(size_t)b * 16 + t]);
+  s = warp_sum(s);
+  if (lane == 0) s_pot[t] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bv = s_pot[0];
+    int bt = 0;
+    for (int u = 1; u < trials; ++u)
+      if (s_pot[u] < bv) {            // np.argmin: first minimum
+        bv = s_pot[u];
+        bt = u;
+      }
+    for (int u = 0; u < 16; ++u) st->pot[u] = u < trials ? s_pot[u] : 0.0;
     st->best = bt;
     st->current_pot = bv;
     center_ids[step] = st->cand[bt];
   }
 }
 
-// closest_i = min(closest_i, D[i][best]); wc_i = w_i * closest_i (the vector whose cumulative sum is searched)
-__global__ void __launch_bounds__(256) km_commit_kernel(const double* __restrict__ D, const PpState* __restrict__ st,
-                                                        const double* __restrict__ w, long long n, double* __restrict__ closest,
-                                                        double* __restrict__ wc) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double c = fmin(closest[i], D[(size_t)i * 16 + st->best]);
-  closest[i] = c;
-  wc[i] = w ? __dmul_rn(w[i], c) : c;
-}
-
-// candidate_ids = clip(searchsorted(cum, rand * current_pot), n - 1)   (side='left': first cum >= value)
-__global__ void __launch_bounds__(32) km_search_kernel(const double* __restrict__ cum, long long n, const double* __restrict__ rand_vals,
-                                                       int trials, PpState* st) {
-  const int t = threadIdx.x;
-  if (t >= 16) return;
-  int id = 0;
-  if (t < trials) {
-    const double v = __dmul_rn(rand_vals[t], st->current_pot);
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (cum[mid] < v) lo = mid + 1;
-      else hi = mid;
-    }
-    id = (int)min(lo, n - 1);
-  }
-  st->cand[t] = id;
-}
 // inclusive prefix sum in a fixed order (the same bits on every run): tiles of 1024 values
 constexpr int kScanTile = 1024;
-__global__ void __launch_bounds__(256) km_scan_tiles_kernel(const double* __restrict__ v, long long n, double* __restrict__ tile_sum) {
+// closest_i = min(closest_i, D[i][best]) and the tile sums of wc_i = w_i * closest_i (the vector whose cumulative sum
+// the next step searches)
+template <int BN>
+__global__ void __launch_bounds__(256) km_commit_tiles_kernel(const double* __restrict__ D, const PpState* __restrict__ st,
+                                                              const double* __restrict__ w, long long n, double* __restrict__ closest,
+                                                              double* __restrict__ wc, double* __restrict__ tile_sum) {
   using BS = cub::BlockScan<double, 256>;
   __shared__ typename BS::TempStorage tmp;
+  const int best = st->best;
   const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * 4;
   double s = 0.0;
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
-    if (base + e < n) s = __dadd_rn(s, v[base + e]);
+  for (int e = 0; e < 4; ++e) {
+    const long long i = base + e;
+    if (i < n) {
+      const double c = fmin(closest[i], D[(size_t)i * BN + best]);
+      closest[i] = c;
+      const double v = w ? __dmul_rn(w[i], c) : c;
+      wc[i] = v;
+      s = __dadd_rn(s, v);
+    }
+  }
   double incl, total;
   BS(tmp).InclusiveSum(s, incl, total);
   if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
-__global__ void km_scan_offsets_kernel(double* __restrict__ tile_sum, int tiles) {   // exclusive, sequential
-  double run = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const double x = tile_sum[t];
-    tile_sum[t] = run;
-    run = __dadd_rn(run, x);
+// exclusive scan of the tile sums: one block, chunks of 1024 tiles with a running carry
+__global__ void __launch_bounds__(256) km_scan_offsets_kernel(double* __restrict__ tile_sum, int tiles) {
+  using BS = cub::BlockScan<double, 256>;
+  __shared__ typename BS::TempStorage tmp;
+  __shared__ double s_carry;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  for (int c0 = 0; c0 < tiles; c0 += 1024) {
+    const int base = c0 + threadIdx.x * 4;
+    double x[4], s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      x[e] = base + e < tiles ? tile_sum[base + e] : 0.0;
+      s = __dadd_rn(s, x[e]);
+    }
+    double excl, total;
+    BS(tmp).ExclusiveSum(s, excl, total);
+    double run = __dadd_rn(s_carry, excl);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (base + e < tiles) tile_sum[base + e] = run;
+      run = __dadd_rn(run, x[e]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = __dadd_rn(s_carry, total);
+    __syncthreads();
   }
 }
 __global__ void __launch_bounds__(256) km_scan_apply_kernel(const double* __restrict__ v, long long n, const double* __restrict__ tile_off,
@@ -420,14 +425,35 @@ __global__ void km_pp_seed_kernel(PpState* st, int first) {
     st->pot[t] = 0.0;
   }
 }
-// candidate rows of the state -> fp64 centre tile (16 x d) + their norms
-__global__ void __launch_bounds__(256) km_gather_state_kernel(const float* __restrict__ X, int d, const PpState* __restrict__ st, int trials,
-                                                              const double* __restrict__ xx, double* __restrict__ C, double* __restrict__ cc) {
+// candidate t of the step: clip(searchsorted(cum, rand_t * current_pot), n - 1) (side='left': first cum >= value;
+// rand_vals == NULL: the seed row already in the state), then its row as fp64 into the candidate tile + its norm
+__global__ void __launch_bounds__(256) km_candidates_kernel(const float* __restrict__ X, int d, long long n, const double* __restrict__ cum,
+                                                            const double* __restrict__ rand_vals, PpState* st, int trials,
+                                                            const double* __restrict__ xx, double* __restrict__ C, double* __restrict__ cc) {
+  __shared__ int s_row;
   const int t = blockIdx.x;
   const bool live = t < trials;
-  const long long r = st->cand[live ? t : 0];
+  if (threadIdx.x == 0) {
+    int id = st->cand[0];
+    if (live && rand_vals) {
+      const double v = __dmul_rn(rand_vals[t], st->current_pot);
+      long long lo = 0, hi = n;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (cum[mid] < v) lo = mid + 1;
+        else hi = mid;
+      }
+      id = (int)min(lo, n - 1);
+    }
+    s_row = id;
+  }
+  __syncthreads();
+  const long long r = s_row;
   for (int c = threadIdx.x; c < d; c += blockDim.x) C[(size_t)t * d + c] = live ? (double)X[(size_t)r * d + c] : 0.0;
-  if (threadIdx.x == 0) cc[t] = live ? xx[r] : 0.0;
+  if (threadIdx.x == 0) {
+    cc[t] = live ? xx[r] : 0.0;
+    if (rand_vals && live) st->cand[t] = (int)r;      // (dead blocks may see either cand[0]: they never use the row)
+  }
 }
 
 // ---- M step
@@ -781,32 +807,36 @@ extern "C" int vatlq_kmeans_pp(const float* X, int64_t n, int d, const double* w
   rc = fill_f64(closest, n, INFINITY, stream);
   if (rc) return rc;
   const int pot_blocks = (int)std::min<long long>(kPotBlocks, (n + 255) / 256);
+  // candidates per step: 8 columns of fp64 tensor-core work when n_local_trials <= 8 (k < 403), else 16
+  const bool narrow = trials <= 8;
+  const int bn = narrow ? 8 : 16;
   GemmArgs g{};
-  g.X = X; g.n = n; g.d = d; g.C = Cbuf; g.m = 16; g.cn = cc; g.xx = xx; g.out = D;
+  g.X = X; g.n = n; g.d = d; g.C = Cbuf; g.m = bn; g.cn = cc; g.xx = xx; g.out = D;
   km_pp_seed_kernel<<<1, 1, 0, stream>>>(st, (int)first_center);
   VQ_LAUNCHED();
   for (int64_t c = 0; c < k; ++c) {
     const int tr = c == 0 ? 1 : trials;       // step 0: the first centre alone (closest = its distances)
-    if (c > 0) {
-      km_scan_tiles_kernel<<<tiles, 256, 0, stream>>>(wc, n, tile_off);
-      VQ_LAUNCHED();
-      km_scan_offsets_kernel<<<1, 1, 0, stream>>>(tile_off, tiles);
+    // (step c > 0: cand[0] of the previous step is dead once `cum` exists; with rand_vals == NULL the state's
+    //  seed row is used, and no block writes the state)
+    km_candidates_kernel<<<bn, 256, 0, stream>>>(X, d, n, cum, c == 0 ? nullptr : rand_vals + (size_t)(c - 1) * trials, st, tr, xx,
+                                                 Cbuf, cc);
+    VQ_LAUNCHED();
+    rc = narrow ? launch_gemm<128, 8, 4, 1, 1>(g, stream) : launch_gemm<128, 16, 4, 1, 1>(g, stream);
+    if (rc) return rc;
+    if (narrow) km_pot_partial_kernel<8><<<pot_blocks, 256, 0, stream>>>(D, closest, w, n, part);
+    else km_pot_partial_kernel<16><<<pot_blocks, 256, 0, stream>>>(D, closest, w, n, part);
+    VQ_LAUNCHED();
+    km_pot_final_kernel<<<1, 512, 0, stream>>>(part, pot_blocks, tr, st, center_ids, (int)c);
+    VQ_LAUNCHED();
+    if (narrow) km_commit_tiles_kernel<8><<<tiles, 256, 0, stream>>>(D, st, w, n, closest, wc, tile_off);
+    else km_commit_tiles_kernel<16><<<tiles, 256, 0, stream>>>(D, st, w, n, closest, wc, tile_off);
+    VQ_LAUNCHED();
+    if (c + 1 < k) {
+      km_scan_offsets_kernel<<<1, 256, 0, stream>>>(tile_off, tiles);
       VQ_LAUNCHED();
       km_scan_apply_kernel<<<tiles, 256, 0, stream>>>(wc, n, tile_off, cum);
       VQ_LAUNCHED();
-      km_search_kernel<<<1, 32, 0, stream>>>(cum, n, rand_vals + (size_t)(c - 1) * trials, tr, st);
-      VQ_LAUNCHED();
     }
-    km_gather_state_kernel<<<16, 256, 0, stream>>>(X, d, st, tr, xx, Cbuf, cc);
-    VQ_LAUNCHED();
-    rc = launch_gemm<128, 16, 4, 1, 1>(g, stream);
-    if (rc) return rc;
-    km_pot_partial_kernel<<<pot_blocks, 256, 0, stream>>>(D, closest, w, n, tr, part);
-    VQ_LAUNCHED();
-    km_pot_final_kernel<<<1, 32, 0, stream>>>(part, pot_blocks, tr, st, center_ids, (int)c);
-    VQ_LAUNCHED();
-    km_commit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(D, st, w, n, closest, wc);
-    VQ_LAUNCHED();
   }
   return 0;
 }

@@ -8,7 +8,7 @@ sklearn draws them (sklearn/cluster/_kmeans.py: `_kmeans_plusplus`), decides con
 path: the embeddings must be a CUDA tensor.
 
 What is reproduced: the labels and therefore the queried rows.  sklearn's centre sums depend on its OpenMP chunking,
-so centre coordinates agree to rounding only (tests/test_gpu_kmeans.py checks labels and picks exactly, centres to
+so centre coordinates of clusters with three or more members agree to rounding only (tests/test_gpu_kmeans.py checks labels and picks exactly, centres to
 1e-9).  The order in which several clusters that became empty in the SAME iteration are re-seeded follows numpy's
 argpartition on the device-computed distances, like sklearn.
 """

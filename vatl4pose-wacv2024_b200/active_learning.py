@@ -13,8 +13,8 @@ evaluation, plotting) is out of scope and is injected or hooked:
 
 Strategy names are the reference's (`opt.uncertainty`, `opt.representativeness`, `opt.filter`,
 ActiveLearning.py:329-401,467-481,533-619).  Uncertainties THC*, WPU*, THC+WPU, HP, TPC, Entropy
-and None, representativeness None / Influence / Random and filters None / Coreset / Diversity /
-Random run here; names without a device path (see _require_accelerated) raise NotImplementedError
+MPE, Margin and None, representativeness None / Influence / Random and filters None / Coreset / Diversity /
+Random / K-Means / weighted run here; names without a device path (see _require_accelerated) raise NotImplementedError
 naming the reference code path to use (dispatch to the reference, never a CPU re-implementation
 of ours).
 """

@@ -34,6 +34,12 @@ def _worker(rank, world, port, n, q):
         ok &= (hn is None) if hi == n else torch.equal(hn, H[hi])
         full = dist.allgather_rows(loc.reshape(hi - lo, -1), n, world)
         ok &= torch.equal(full, H.reshape(n, -1))
+        # 1-D int32 shards (the K-Means labels of the row-sharded assignment step, kmeans.py) + SUM of the change counts
+        lab = (torch.arange(n, dtype=torch.int32) * 7) % 5
+        ok &= torch.equal(dist.allgather_rows(lab[lo:hi], n, world), lab)
+        cnt = torch.tensor([hi - lo], dtype=torch.int32)
+        td.all_reduce(cnt, op=td.ReduceOp.SUM)
+        ok &= int(cnt.item()) == n
         # fusion statistics: {min, -max} pairs reduce with one MIN
         v = H[lo:hi].reshape(-1).double()
         st = torch.stack([v.min(), (-v).min()])

@@ -71,7 +71,8 @@ def main():
     lo, hi = vd.shard_range(n, rank, world)
     to = lambda a, sl=slice(None): torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev)
     for unc, rep, flt in (("TPC", "Influence", "None"), ("Entropy", "None", "Diversity"), ("MPE", "None", "None"),
-                          ("Margin", "Influence", "Diversity"), ("HP", "Influence", "Coreset"), ("None", "Influence", "Coreset")):
+                          ("Margin", "Influence", "Diversity"), ("HP", "Influence", "Coreset"), ("None", "Influence", "Coreset"),
+                          ("THC", "None", "K-Means"), ("THC", "Influence", "weighted")):
         Hs = Hpos if unc == "Entropy" else H
         rule = "dist" if unc == "None" else "w_unc"
         kw = dict(uncertainty=unc, representativeness=rep, filter=flt, rule=rule, first_pick=-1)

@@ -128,12 +128,14 @@ class Comm:
 def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_local, ae_weights, labeled_global,
                       n: int, k: int, moks: float = 0.0, lam: float = 0.01, uncertainty: str = "THC+WPU",
                       thc_vs_wpu: str = "const", rule: str = "w_unc", batch: int = 16, comm: Comm | None = None,
-                      group=None, first_pick: int = -1, representativeness: str = "None", filter: str = "Coreset"):
+                      group=None, first_pick: int = -1, representativeness: str = "None", filter: str = "Coreset",
+                      w_unc: float = 1.0):
     """One query over a pool sharded across the ranks of `group` (one process per GPU).
     Every rank passes its slice of the pool and gets the same global pick list back.
     uncertainty: any accelerated name (THC*, WPU*, THC+WPU, HP, TPC, Entropy, MPE, Margin, None);
     representativeness: "None" or "Influence" (ActiveLearning.py:467-477); filter: "Coreset" (:609-614),
-    "None" (top-k, :533-534) or "Diversity" (:581-590).  Scoring is sharded (halo frame / halo coordinates for
+    "None" (top-k, :533-534), "Diversity" (:581-590), "K-Means" (:593-608) or "weighted" (:553-580; w_unc = cfg.VAL.W_UNC;
+    the assignment step of Lloyd is sharded by rows, seeding and the M step run replicated).  Scoring is sharded (halo frame / halo coordinates for
     THC / TPC, MIN all-reduces for the normalisations, a SUM all-reduce of the cosine column sums for
     Influence); the fused scores are all-gathered (8 B per item) and the final ordering runs replicated."""
     from . import ops
@@ -185,6 +187,23 @@ def distributed_query(H_local, boxes_local, is_prev_local, is_next_local, X_loca
             cand = torch.sort(ops.rank_scores(score, unl_g, descending=True, count=8 * k)).values
             div = ops.cosine_rowsum(X, rows=cand)
             picks = cand[ops.rank_scores(div, None, descending=False, count=k)]
+    elif filter in ("K-Means", "weighted"):                                  # (:553-580, 593-608)
+        from . import kmeans as KM
+        st = None
+        X = allgather_rows(X_local, n, world, group)
+        cand = np.setdiff1d(np.arange(n, dtype=np.int64), lab)               # sorted unlabelled ids (:535-536)
+        cand_t = torch.from_numpy(cand).to(dev)
+        emb = X[cand_t]
+        kk = min(k, int(cand.size))
+        if filter == "weighted":
+            eidx = torch.as_tensor(KM.unique_rows_first_index(emb), dtype=torch.int64, device=dev)
+            emb = emb[eidx]
+            weight = (1 + w_unc * qp.combine_weight * score[cand_t])[eidx].contiguous()
+            kk = min(kk, int(emb.shape[0]))
+            res = KM.kmeans_fit_select(emb, kk, sample_weight=weight, group=fuse_group)
+        else:
+            res = KM.kmeans_fit_select(emb, kk, group=fuse_group)
+        picks = torch.as_tensor([int(cand[i]) for i in res.query_rows], dtype=torch.int64, device=dev)
     else:
         raise ValueError("Filter type is not supported by distributed_query")
     return QueryResult(picks=picks, thc=qp.thc, wpu=qp.wpu, peak_mean=qp.peak_mean, kpts=qp.kpts, unc=score,

@@ -43,9 +43,12 @@ def _f64(*shape, dev):
 
 
 def kmeans_fit_select(X: torch.Tensor, n_clusters: int, sample_weight: torch.Tensor | None = None, random_state: int = 318,
-                      max_iter: int = 300, tol: float = 1e-4) -> KMeansResult:
+                      max_iter: int = 300, tol: float = 1e-4, group=None) -> KMeansResult:
     """`KMeans(n_clusters, random_state=random_state).fit_predict(X, sample_weight)` (k-means++ init, n_init = 1,
-    Lloyd) + the per-cluster closest member.  X (n,d) fp32 CUDA, sample_weight (n,) fp64 CUDA or None."""
+    Lloyd) + the per-cluster closest member.  X (n,d) fp32 CUDA, sample_weight (n,) fp64 CUDA or None.
+    group: a torch.distributed group whose ranks all hold the SAME X: the assignment GEMM (the dominant step of a
+    Lloyd iteration) is sharded by rows and the labels are all-gathered; seeding and the M step replay identically
+    on every rank (deterministic kernels), so every rank returns the same result as a single GPU."""
     X = _cuda(X, torch.float32, "X")
     if X.dim() != 2:
         raise _lib.VatlqError("X must be (n,d)")
@@ -92,9 +95,27 @@ def kmeans_fit_select(X: torch.Tensor, n_clusters: int, sample_weight: torch.Ten
         dis = _f64(n, dev=dev)
         strict, n_iter, relocations = False, 0, 0
 
+        world = 1
+        if group is not None:
+            import torch.distributed as td
+            from .dist import allgather_rows, shard_range
+            world = td.get_world_size(group)
+            lo, hi = shard_range(n, td.get_rank(group), world)
+
         def assign(into, against, counter):
-            _lib.check(L.vatlq_kmeans_assign(_ptr(X), n, d, _ptr(centers), k, _ptr(into), _ptr(against), _ptr(counter),
-                                             _ptr(ws), wsb, st), "vatlq_kmeans_assign")
+            if world == 1:
+                _lib.check(L.vatlq_kmeans_assign(_ptr(X), n, d, _ptr(centers), k, _ptr(into), _ptr(against), _ptr(counter),
+                                                 _ptr(ws), wsb, st), "vatlq_kmeans_assign")
+                return
+            if hi > lo:                                             # this rank's rows only
+                _lib.check(L.vatlq_kmeans_assign(_ptr(X[lo:hi]), hi - lo, d, _ptr(centers), k, _ptr(into[lo:hi]),
+                                                 None if against is None else _ptr(against[lo:hi]), _ptr(counter),
+                                                 _ptr(ws), wsb, st), "vatlq_kmeans_assign")
+            elif counter is not None:
+                counter.zero_()
+            into[:n].copy_(allgather_rows(into[lo:hi], n, world, group))
+            if counter is not None:
+                td.all_reduce(counter, op=td.ReduceOp.SUM, group=group)
 
         def average(argmax_w):
             _lib.check(L.vatlq_kmeans_average(_ptr(sums), _ptr(wsum), k, d, argmax_w, _ptr(mean), _ptr(cc), _ptr(cc_new),

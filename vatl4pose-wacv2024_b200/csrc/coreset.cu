@@ -202,6 +202,17 @@ constexpr int kDepth = VQ_DEPTH;     // super-steps of x in flight per lane (reg
 #endif
 constexpr int kPrefetch = VQ_PREFETCH;  // super-steps the L2 prefetch cursor runs ahead of the ring
 
+// Programmatic dependent launch: the kernels of a round (candidate tiles + planner, segment filter, paired pass, solo
+// pass) are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each starts with pdl_enter(): wait until
+// the previous kernel has completed and flushed (so the data flow is exactly the stream order), then let the NEXT
+// kernel's CTAs be scheduled as SMs free up — they sit in their own pdl_enter() until this grid is done.  What is
+// saved is the launch / scheduling latency of every kernel boundary of the round.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c[0]), "+d"(c[1])
@@ -763,6 +774,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) pass_kernel_tma(PassArgs a) {
   unsigned int* s_flagged = reinterpret_cast<unsigned int*>(s_tiles + kMaxTilesCta);
   int* s_na = reinterpret_cast<int*>(s_flagged + kMaxTilesCta / 32);
 
+  pdl_enter();
   const int total = a.n_centers ? *a.n_centers : a.n_centers_imm;
   const int crank = PAIR ? (int)cluster_ctarank() : 0;
   bool final_pass;
@@ -1510,6 +1522,7 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
   __shared__ __align__(16) double s_part[2][kSeg][64];
   __shared__ double s_xxc[2 * kB];
   __shared__ unsigned int s_last;
+  pdl_enter();
   if (ctl->n_picked >= ctl->k) {       // (uniform over the grid: nobody takes a ticket)
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctl->nb = 0;
     return;
@@ -2030,20 +2043,31 @@ static int pair_grid() {
 
 // the paired pass of a 16-pick round (d = 2048 only): applies picks [0, nb) when nb > 8, reading X once
 // (filter = true: the same tile machine over the segment anchors, writing both centre groups' skip flags)
+// VATLQ_PDL=0: plain stream-ordered launches (measurement switch)
+static bool pdl_on() {
+  static const bool on = []() {
+    const char* e = getenv("VATLQ_PDL");
+    return !(e && (!strcmp(e, "0") || !strcmp(e, "off")));
+  }();
+  return on;
+}
+
 static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
-                            bool filter = false) {
+                            bool filter = false, bool pdl = false) {
   if (int e = configure_pass()) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)pair_grid());
   cfg.blockDim = dim3(kWsThreads);
   cfg.dynamicSmemBytes = kWsSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute at{};
-  at.id = cudaLaunchAttributeClusterDimension;
-  at.val.clusterDim.x = 2;
-  at.val.clusterDim.y = at.val.clusterDim.z = 1;
-  cfg.attrs = &at;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute at[2] = {};
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_on()) ? 2 : 1;
   if (ev0) cudaEventRecord(ev0, stream);
   if (filter) VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true, true>, a));
   else VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, true, false>, a));
@@ -2052,11 +2076,23 @@ static int launch_pass_pair(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = 
   return 0;
 }
 
-static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+static int launch_pass(PassArgs& a, cudaStream_t stream, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, bool pdl = false) {
   if (int e = configure_pass()) return e;
   if (ev0) cudaEventRecord(ev0, stream);
   const bool fast = a.d4 == kSeg * 4 * 16 && a.dots != nullptr;   // d = 2048
-  if (fast) pass_kernel_tma<16, false><<<sm_count(), kWsThreads, kWsSmem, stream>>>(a);
+  if (fast && pdl && pdl_on()) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)sm_count());
+    cfg.blockDim = dim3(kWsThreads);
+    cfg.dynamicSmemBytes = kWsSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    VQ_CUDA(cudaLaunchKernelEx(&cfg, pass_kernel_tma<16, false, false>, a));
+  } else if (fast) pass_kernel_tma<16, false><<<sm_count(), kWsThreads, kWsSmem, stream>>>(a);
   else if ((a.d4 & 3) != 0) pass_kernel_generic<true><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   else pass_kernel_generic<false><<<sm_count(), kPassThreads, pass_smem_bytes(a.S), stream>>>(a);
   if (ev1) cudaEventRecord(ev1, stream);
@@ -2265,6 +2301,8 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
   const bool tma_filter = (row_hi - row_lo) >= tma_filter_min;
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
+    // the same shared-memory carve-out as the pass kernels on either side of it: no SM reconfiguration between them
+    VQ_CUDA(cudaFuncSetAttribute(pairs_plan_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     pairs_cfg = true;
   }
@@ -2333,8 +2371,22 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
       if (nbk > 1) {
         dim3 pg(kCap / kB, 4);
         if (fast_d) {
-          pairs_plan_kernel<16><<<dim3((unsigned)sm_count(), 1), kSeg * 32, 0, stream>>>(X, G.d4, xx, blocks, send, hist, (long long*)out_idx, ctl, Dcc,
-                                                             mail, seq0 + round_no);
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3((unsigned)sm_count(), 1);
+          cfg.blockDim = dim3(kSeg * 32);
+          cfg.stream = stream;
+          cudaLaunchAttribute at{};
+          at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at.val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = &at;
+          cfg.numAttrs = pdl_on() ? 1 : 0;
+          const cudaError_t le = cudaLaunchKernelEx(&cfg, pairs_plan_kernel<16>, X, G.d4, (const double*)xx, blocks, send, hist,
+                                                    (long long*)out_idx, ctl, Dcc, mail, (unsigned long long)(seq0 + round_no));
+          if (le != cudaSuccess) {
+            snprintf(g_err, sizeof(g_err), "pairs_plan launch failed: %s", cudaGetErrorString(le));
+            rc = (int)le;
+            break;
+          }
         } else {
           if (p2p) wait_blocks_kernel<<<1, 1, 0, stream>>>(mail, ctl, seq0 + round_no);
           pairs_kernel<<<pg, 256, pairs_smem, stream>>>(X, G.d4, G.nss, G.S, G.guard, xx, blocks, ctl, Dcc);
@@ -2353,7 +2405,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         if (use_pair && tma_filter) {   // the pass's own TMA / DMMA tile machine over the anchor rows (bandwidth-bound)
           a.seg_start = P.seg_start; a.seg_r = P.seg_r; a.nseg = &P.pc->nseg; a.seg_skip_out = P.seg_skip;
           a.skip_stride = P.skip_stride;
-          rc = launch_pass_pair(a, stream, nullptr, nullptr, true);
+          rc = launch_pass_pair(a, stream, nullptr, nullptr, true, true);
         } else {
           rc = launch_filter(P, a, stream, (nbk + kB - 1) / kB);
         }
@@ -2362,7 +2414,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
         const bool timed = g_prof.on && g_prof.used + 2 <= g_prof.ev.size() && g_prof.used / 2 < 1024;
         if (timed) a.did_work = flags + g_prof.used / 2;
         cudaEvent_t e0 = timed ? g_prof.ev[g_prof.used] : nullptr, e1 = timed ? g_prof.ev[g_prof.used + 1] : nullptr;
-        const int r = pair ? launch_pass_pair(a, stream, e0, e1) : launch_pass(a, stream, e0, e1);
+        const int r = pair ? launch_pass_pair(a, stream, e0, e1, false, true) : launch_pass(a, stream, e0, e1, true);
         if (timed) g_prof.used += 2;
         return r;
       };

@@ -83,6 +83,35 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Chains of short kernels (a core-set round: candidate tiles + planner, segment filter, paired pass, solo pass; a
+// k-means++ step: seven kernels) are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each starts with pdl_enter(): wait until
+// the previous kernel has completed and flushed (so the data flow is exactly the stream order), then let the NEXT
+// kernel's CTAs be scheduled as SMs free up — they sit in their own pdl_enter() until this grid is done.  What is
+// saved is the launch / scheduling latency of every kernel boundary of the round.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// launch `kernel` as a programmatic dependent of the previous kernel in `stream` (pdl = false: plain launch)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- mbarrier / TMA bulk copy (sm_90+)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

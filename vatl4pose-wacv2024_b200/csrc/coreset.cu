@@ -202,17 +202,6 @@ constexpr int kDepth = VQ_DEPTH;     // super-steps of x in flight per lane (reg
 #endif
 constexpr int kPrefetch = VQ_PREFETCH;  // super-steps the L2 prefetch cursor runs ahead of the ring
 
-// Programmatic dependent launch: the kernels of a round (candidate tiles + planner, segment filter, paired pass, solo
-// pass) are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each starts with pdl_enter(): wait until
-// the previous kernel has completed and flushed (so the data flow is exactly the stream order), then let the NEXT
-// kernel's CTAs be scheduled as SMs free up — they sit in their own pdl_enter() until this grid is done.  What is
-// saved is the launch / scheduling latency of every kernel boundary of the round.  Without the launch attribute both
-// instructions are no-ops.
-__device__ __forceinline__ void pdl_enter() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c[0]), "+d"(c[1])
@@ -1439,7 +1428,7 @@ __global__ void __launch_bounds__(256) pairs_kernel(const float* __restrict__ X,
 }
 
 __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double* Dcc, unsigned int* hist,
-                          long long* out_idx, Ctl* ctl);
+                          long long* out_idx, Ctl* ctl, double* s_D = nullptr, int s_D_cap = 0);
 
 // Candidate x candidate distances, symmetric: only the tile pairs (column block cb <= row tile t) are computed and
 // every 8 x 8 block is written twice (d is symmetric; both halves hold the SAME bits, so the planner may read rows).
@@ -1513,12 +1502,13 @@ __device__ __forceinline__ void pairs_tiles(const float* __restrict__ X, int d4,
 // exchange warp w finishes row w of the tile: lane j writes d(row, centre j).
 // The last CTA of the grid to finish runs the planner (plan_body) on the completed matrix, so a
 // round needs no separate plan launch.
+constexpr int kPlanSmem = 208 * 1024;    // dynamic shared memory of pairs_plan_kernel: the planner's staged distance rows
 template <int STEPS>
 __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* __restrict__ X, int d4,
                                                                   const double* __restrict__ xx, const RankBlock* blocks,
                                                                   RankBlock* send, unsigned int* hist, long long* out_idx,
                                                                   Ctl* ctl, double* __restrict__ Dcc, Mailbox* mail,
-                                                                  unsigned long long seq) {
+                                                                  unsigned long long seq, int plan_smem_doubles) {
   __shared__ __align__(16) double s_part[2][kSeg][64];
   __shared__ double s_xxc[2 * kB];
   __shared__ unsigned int s_last;
@@ -1559,7 +1549,8 @@ __global__ void __launch_bounds__(kSeg * 32, 1) pairs_plan_kernel(const float* _
       t2 = gtime_ns();
       ctl->stat_ns_tiles += t2 - *((volatile unsigned long long*)&ctl->t_start);
     }
-    plan_body(blocks, send, Dcc, hist, out_idx, ctl);
+    extern __shared__ __align__(16) double s_plan_dyn[];
+    plan_body(blocks, send, Dcc, hist, out_idx, ctl, s_plan_dyn, plan_smem_doubles);
     __syncthreads();
     if (threadIdx.x == 0) ctl->stat_ns_plan += gtime_ns() - t2;
   }
@@ -1669,8 +1660,11 @@ __device__ void choose_theta(const unsigned int* __restrict__ hist, double U, do
 constexpr int kPlanThreads = 256;
 constexpr int kPerThread = kCap / kPlanThreads;   // candidates per planner thread (strided: c = tid + 256 j)
 
+// s_D (optional, s_D_cap doubles of shared memory): the candidate x candidate distances of as many centre rows as
+// fit are staged there with cp.async while the list is read, so that a pick's row costs a shared-memory read instead
+// of an L2 round trip on the sequential pick chain (a list of <= 163 candidates fits whole in 208 KB)
 __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double* Dcc, unsigned int* hist,
-                          long long* out_idx, Ctl* ctl) {
+                          long long* out_idx, Ctl* ctl, double* s_D, int s_D_cap) {
   __shared__ Best s_b[2][8];
   __shared__ int s_pos[2][8];
   __shared__ double s_theta;
@@ -1709,6 +1703,19 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     if (tid == 0) fallback_pick(blocks, world, v.fallback, send, out_idx, ctl);
     return;
   }
+  // stage the rows of centres [0, staged) of Dcc (columns [0, total)), 16 bytes per cp.async
+  const int dstride = (v.total + 1) & ~1;
+  const int staged = (s_D != nullptr && dstride > 0) ? min(v.total, s_D_cap / dstride) : 0;
+  {
+    const int per_row = dstride >> 1;
+    for (int q = tid; q < staged * per_row; q += kPlanThreads) {
+      const int r = q / per_row, c2 = q - r * per_row;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_D + (size_t)r * dstride + 2 * c2)),
+                   "l"(Dcc + (size_t)r * kCap + 2 * c2)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   // candidates c = tid + 256 j live in registers
   long long idx[kPerThread];
   double m[kPerThread], u[kPerThread], sc[kPerThread];
@@ -1728,6 +1735,8 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
       sc[j] = blocks[r].score[q];
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   int nb = 0;
   for (int b = 0; b < maxpicks; ++b) {
     // block arg-max: thread-local, warp butterfly, ONE barrier, every warp reduces the 8 warp winners
@@ -1782,11 +1791,13 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     }
     nb += 1;
     const double* drow = Dcc + (size_t)wpos * kCap;   // drow[c] = d(row c, centre = the winner), coalesced
+    const double* srow = s_D + (size_t)wpos * dstride;
+    const bool in_smem = wpos < staged;
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
       const int c = tid + kPlanThreads * j;
       if (c < v.total) {
-        m[j] = fmin(m[j], __ldcg(drow + c));
+        m[j] = fmin(m[j], in_smem ? srow[c] : __ldcg(drow + c));
         if (c == wpos) u[j] = 0.0;
         sc[j] = score_of(rule, wd, wu, m[j], u[j]);
       }
@@ -2299,10 +2310,12 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     return e ? atoll(e) : 0LL;
   }();
   const bool tma_filter = (row_hi - row_lo) >= tma_filter_min;
+  static const size_t plan_smem = getenv("VATLQ_PLAN_SMEM") ? (size_t)atoi(getenv("VATLQ_PLAN_SMEM")) * 1024 : (size_t)kPlanSmem;   // 0: L2 path
   static bool pairs_cfg = false;
   if (!pairs_cfg) {
     // the same shared-memory carve-out as the pass kernels on either side of it: no SM reconfiguration between them
     VQ_CUDA(cudaFuncSetAttribute(pairs_plan_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    VQ_CUDA(cudaFuncSetAttribute(pairs_plan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlanSmem));
     VQ_CUDA(cudaFuncSetAttribute(pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     pairs_cfg = true;
   }
@@ -2374,6 +2387,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
           cudaLaunchConfig_t cfg{};
           cfg.gridDim = dim3((unsigned)sm_count(), 1);
           cfg.blockDim = dim3(kSeg * 32);
+          cfg.dynamicSmemBytes = plan_smem;
           cfg.stream = stream;
           cudaLaunchAttribute at{};
           at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -2381,7 +2395,7 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
           cfg.attrs = &at;
           cfg.numAttrs = pdl_on() ? 1 : 0;
           const cudaError_t le = cudaLaunchKernelEx(&cfg, pairs_plan_kernel<16>, X, G.d4, (const double*)xx, blocks, send, hist,
-                                                    (long long*)out_idx, ctl, Dcc, mail, (unsigned long long)(seq0 + round_no));
+                                                    (long long*)out_idx, ctl, Dcc, mail, (unsigned long long)(seq0 + round_no), (int)(plan_smem / 8));
           if (le != cudaSuccess) {
             snprintf(g_err, sizeof(g_err), "pairs_plan launch failed: %s", cudaGetErrorString(le));
             rc = (int)le;

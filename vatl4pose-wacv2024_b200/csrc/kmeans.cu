@@ -25,6 +25,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -81,6 +83,7 @@ struct GemmArgs {
 
 template <int BM, int BN, int WM, int WN, int MODE>
 __global__ void __launch_bounds__(WM * WN * 32) km_gemm_kernel(GemmArgs a) {
+  pdl_enter();
   constexpr int kThreads = WM * WN * 32;
   constexpr int TM = BM / WM / 8, TN = BN / WN / 8;
   extern __shared__ __align__(16) unsigned char km_smem[];
@@ -285,6 +288,7 @@ constexpr int kPotBlocks = 512;
 template <int BN>
 __global__ void __launch_bounds__(256) km_pot_partial_kernel(const double* __restrict__ D, const double* __restrict__ closest,
                                                              const double* __restrict__ w, long long n, double* __restrict__ part) {
+  pdl_enter();
   __shared__ double s_p[8][BN];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double p[BN];
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(256) km_pot_partial_kernel(const double* __res
 // potentials of the candidates (warp t sums the partials of candidate t in a fixed order), best = first minimum
 __global__ void __launch_bounds__(512) km_pot_final_kernel(const double* __restrict__ part, int blocks, int trials, PpState* st,
                                                            int* __restrict__ center_ids, int step) {
+  pdl_enter();
   __shared__ double s_pot[16];
   const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0.0;
@@ -349,6 +354,7 @@ template <int BN>
 __global__ void __launch_bounds__(256) km_commit_tiles_kernel(const double* __restrict__ D, const PpState* __restrict__ st,
                                                               const double* __restrict__ w, long long n, double* __restrict__ closest,
                                                               double* __restrict__ wc, double* __restrict__ tile_sum) {
+  pdl_enter();
   using BS = cub::BlockScan<double, 256>;
   __shared__ typename BS::TempStorage tmp;
   const int best = st->best;
@@ -371,6 +377,7 @@ __global__ void __launch_bounds__(256) km_commit_tiles_kernel(const double* __re
 }
 // exclusive scan of the tile sums: one block, chunks of 1024 tiles with a running carry
 __global__ void __launch_bounds__(256) km_scan_offsets_kernel(double* __restrict__ tile_sum, int tiles) {
+  pdl_enter();
   using BS = cub::BlockScan<double, 256>;
   __shared__ typename BS::TempStorage tmp;
   __shared__ double s_carry;
@@ -399,6 +406,7 @@ __global__ void __launch_bounds__(256) km_scan_offsets_kernel(double* __restrict
 }
 __global__ void __launch_bounds__(256) km_scan_apply_kernel(const double* __restrict__ v, long long n, const double* __restrict__ tile_off,
                                                             double* __restrict__ cum) {
+  pdl_enter();
   using BS = cub::BlockScan<double, 256>;
   __shared__ typename BS::TempStorage tmp;
   const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * 4;
@@ -430,6 +438,7 @@ __global__ void km_pp_seed_kernel(PpState* st, int first) {
 __global__ void __launch_bounds__(256) km_candidates_kernel(const float* __restrict__ X, int d, long long n, const double* __restrict__ cum,
                                                             const double* __restrict__ rand_vals, PpState* st, int trials,
                                                             const double* __restrict__ xx, double* __restrict__ C, double* __restrict__ cc) {
+  pdl_enter();
   __shared__ int s_row;
   const int t = blockIdx.x;
   const bool live = t < trials;
@@ -713,7 +722,7 @@ __global__ void __launch_bounds__(256) km_mean_kernel(const double* __restrict__
 }
 
 template <int BM, int BN, int WM, int WN, int MODE>
-static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+static int launch_gemm(const GemmArgs& a, cudaStream_t stream, bool pdl = false) {
   const size_t smem = kStages * GemmStage<BM, BN>::kBytes;
   static bool configured = false;
   if (!configured) {
@@ -721,8 +730,8 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const unsigned grid = (unsigned)((a.n + BM - 1) / BM);
-  km_gemm_kernel<BM, BN, WM, WN, MODE><<<grid, WM * WN * 32, smem, stream>>>(a);
-  VQ_LAUNCHED();
+  VQ_CUDA(launch_pdl(km_gemm_kernel<BM, BN, WM, WN, MODE>, dim3(grid), dim3(WM * WN * 32), smem, stream, pdl, a));
+  g_launches.fetch_add(1);
   return 0;
 }
 
@@ -814,28 +823,36 @@ extern "C" int vatlq_kmeans_pp(const float* X, int64_t n, int d, const double* w
   g.X = X; g.n = n; g.d = d; g.C = Cbuf; g.m = bn; g.cn = cc; g.xx = xx; g.out = D;
   km_pp_seed_kernel<<<1, 1, 0, stream>>>(st, (int)first_center);
   VQ_LAUNCHED();
+  static const bool pdl = []() {
+    const char* e = getenv("VATLQ_PDL");
+    return !(e && (!strcmp(e, "0") || !strcmp(e, "off")));
+  }();
   for (int64_t c = 0; c < k; ++c) {
     const int tr = c == 0 ? 1 : trials;       // step 0: the first centre alone (closest = its distances)
-    // (step c > 0: cand[0] of the previous step is dead once `cum` exists; with rand_vals == NULL the state's
-    //  seed row is used, and no block writes the state)
-    km_candidates_kernel<<<bn, 256, 0, stream>>>(X, d, n, cum, c == 0 ? nullptr : rand_vals + (size_t)(c - 1) * trials, st, tr, xx,
-                                                 Cbuf, cc);
-    VQ_LAUNCHED();
-    rc = narrow ? launch_gemm<128, 8, 4, 1, 1>(g, stream) : launch_gemm<128, 16, 4, 1, 1>(g, stream);
+    // (with rand_vals == NULL the state's seed row is used and no block writes the state).  Every kernel of the chain
+    // is a programmatic dependent of the one before it (pdl_enter() at kernel entry keeps the data flow in stream order)
+    VQ_CUDA(launch_pdl(km_candidates_kernel, dim3(bn), dim3(256), 0, stream, pdl && c > 0, X, d, (long long)n, (const double*)cum,
+                       c == 0 ? (const double*)nullptr : rand_vals + (size_t)(c - 1) * trials, st, tr, (const double*)xx, Cbuf, cc));
+    rc = narrow ? launch_gemm<128, 8, 4, 1, 1>(g, stream, pdl) : launch_gemm<128, 16, 4, 1, 1>(g, stream, pdl);
     if (rc) return rc;
-    if (narrow) km_pot_partial_kernel<8><<<pot_blocks, 256, 0, stream>>>(D, closest, w, n, part);
-    else km_pot_partial_kernel<16><<<pot_blocks, 256, 0, stream>>>(D, closest, w, n, part);
-    VQ_LAUNCHED();
-    km_pot_final_kernel<<<1, 512, 0, stream>>>(part, pot_blocks, tr, st, center_ids, (int)c);
-    VQ_LAUNCHED();
-    if (narrow) km_commit_tiles_kernel<8><<<tiles, 256, 0, stream>>>(D, st, w, n, closest, wc, tile_off);
-    else km_commit_tiles_kernel<16><<<tiles, 256, 0, stream>>>(D, st, w, n, closest, wc, tile_off);
-    VQ_LAUNCHED();
+    if (narrow)
+      VQ_CUDA(launch_pdl(km_pot_partial_kernel<8>, dim3(pot_blocks), dim3(256), 0, stream, pdl, (const double*)D, (const double*)closest, w,
+                         (long long)n, part));
+    else
+      VQ_CUDA(launch_pdl(km_pot_partial_kernel<16>, dim3(pot_blocks), dim3(256), 0, stream, pdl, (const double*)D, (const double*)closest, w,
+                         (long long)n, part));
+    VQ_CUDA(launch_pdl(km_pot_final_kernel, dim3(1), dim3(512), 0, stream, pdl, (const double*)part, pot_blocks, tr, st, center_ids, (int)c));
+    if (narrow)
+      VQ_CUDA(launch_pdl(km_commit_tiles_kernel<8>, dim3(tiles), dim3(256), 0, stream, pdl, (const double*)D, (const PpState*)st, w, (long long)n,
+                         closest, wc, tile_off));
+    else
+      VQ_CUDA(launch_pdl(km_commit_tiles_kernel<16>, dim3(tiles), dim3(256), 0, stream, pdl, (const double*)D, (const PpState*)st, w, (long long)n,
+                         closest, wc, tile_off));
+    g_launches.fetch_add(4);
     if (c + 1 < k) {
-      km_scan_offsets_kernel<<<1, 256, 0, stream>>>(tile_off, tiles);
-      VQ_LAUNCHED();
-      km_scan_apply_kernel<<<tiles, 256, 0, stream>>>(wc, n, tile_off, cum);
-      VQ_LAUNCHED();
+      VQ_CUDA(launch_pdl(km_scan_offsets_kernel, dim3(1), dim3(256), 0, stream, pdl, tile_off, tiles));
+      VQ_CUDA(launch_pdl(km_scan_apply_kernel, dim3(tiles), dim3(256), 0, stream, pdl, (const double*)wc, (long long)n, (const double*)tile_off, cum));
+      g_launches.fetch_add(2);
     }
   }
   return 0;

@@ -115,7 +115,7 @@ __device__ __forceinline__ float entr_f32(float p) {
 }
 
 template <int NV>  // NV float4 per lane when the map is NV*128 pixels, 0: generic (second read from L2)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 entropy_kernel(const float* __restrict__ H, int64_t maps, int npx, float* __restrict__ per_map) {
   const int lane = threadIdx.x & 31;
   const int64_t mi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -139,20 +139,42 @@ entropy_kernel(const float* __restrict__ H, int64_t maps, int npx, float* __rest
     }
     acc += (double)s;
     const float S = (float)warp_sum(acc);   // np.sum(pk) is fp32
-    // p = x / S as x * (1/S) when 1/S is a normal number (within 1 ulp of numpy's quotient), else
-    // the IEEE division (S == 0 -> inf / NaN exactly like numpy)
-    const float rS = __frcp_rn(S);
-    const bool mul = fabsf(rS) > 1e-30f && fabsf(rS) < 1e30f;
-    double ea = 0.0;
+    if (S > 1e-10f && S < 1e30f) {
+      // ordinary map (positive finite sum; a NaN pixel makes S NaN and takes the other branch):
+      //   sum_i entr(x_i / S) = ln S - (ln 2 / S) * sum_i x_i lg2 x_i        (sum_i x_i / S = 1 to fp32 rounding)
+      // one MUFU + four ALU instructions per pixel instead of twelve; within 2e-7 of the elementwise form
+      // (checked against scipy on the golden maps).  Any negative pixel makes the reference's sum -inf.
+      double ta = 0.0;
+      float vmin = INFINITY;
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      float4 p;
-      if (mul) p = make_float4(v[q].x * rS, v[q].y * rS, v[q].z * rS, v[q].w * rS);
-      else p = make_float4(__fdiv_rn(v[q].x, S), __fdiv_rn(v[q].y, S), __fdiv_rn(v[q].z, S), __fdiv_rn(v[q].w, S));
-      const float e4 = (entr_f32(p.x) + entr_f32(p.y)) + (entr_f32(p.z) + entr_f32(p.w));
-      ea += (double)e4;
+      for (int q = 0; q < NV; ++q) {
+        const float4 x = v[q];
+        const float t0 = x.x > 1e-30f ? x.x * __log2f(x.x) : 0.f, t1 = x.y > 1e-30f ? x.y * __log2f(x.y) : 0.f;
+        const float t2 = x.z > 1e-30f ? x.z * __log2f(x.z) : 0.f, t3 = x.w > 1e-30f ? x.w * __log2f(x.w) : 0.f;
+        vmin = fminf(vmin, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
+        ta += (double)((t0 + t1) + (t2 + t3));
+      }
+      const double T = warp_sum(ta);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      const double ln2 = 0.69314718055994531;
+      e = (vmin < 0.f) ? -INFINITY : (float)((double)__log2f(S) * ln2 - (ln2 / (double)S) * T);
+    } else {
+      // p = x / S as x * (1/S) when 1/S is a normal number (within 1 ulp of numpy's quotient), else
+      // the IEEE division (S == 0 -> inf / NaN exactly like numpy)
+      const float rS = __frcp_rn(S);
+      const bool mul = fabsf(rS) > 1e-30f && fabsf(rS) < 1e30f;
+      double ea = 0.0;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        float4 p;
+        if (mul) p = make_float4(v[q].x * rS, v[q].y * rS, v[q].z * rS, v[q].w * rS);
+        else p = make_float4(__fdiv_rn(v[q].x, S), __fdiv_rn(v[q].y, S), __fdiv_rn(v[q].z, S), __fdiv_rn(v[q].w, S));
+        const float e4 = (entr_f32(p.x) + entr_f32(p.y)) + (entr_f32(p.z) + entr_f32(p.w));
+        ea += (double)e4;
+      }
+      e = (float)warp_sum(ea);
     }
-    e = (float)warp_sum(ea);
   } else {
     for (int i = lane; i < npx; i += 32) acc += (double)mp[i];
     const float S = (float)warp_sum(acc);

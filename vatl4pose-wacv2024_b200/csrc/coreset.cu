@@ -75,6 +75,8 @@ struct Ctl {
   unsigned long long t_start, stat_ns_wait, stat_ns_tiles, stat_ns_plan;
   // phases of the (paired or solo) pass as seen by CTA 0 (ns, summed): prologue, tile loop, row finishing, publishing
   unsigned long long stat_ns_pass[4];
+  // phases of the planner (ns, summed): theta + histogram clear, candidate records + distance rows staged, pick loop, tail
+  unsigned long long stat_ns_planph[4];
 };
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
@@ -1675,6 +1677,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     return;
   }
   const int world = ctl->world;
+  const unsigned long long tp_begin = (tid == 0) ? gtime_ns() : 0ULL;
   // ---- theta of the list the coming pass emits (window the histogram was built with: the
   // U, W this kernel has not updated yet), then clear the histogram for that pass
   {
@@ -1693,6 +1696,8 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
       ctl->emit_mode = s_mode;
     }
   }
+  unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
+  if (tid == 0) tp1 = gtime_ns();
   const CandView v = view_of(blocks, world);
   const int rule = ctl->rule;
   const double wd = ctl->wd, wu = ctl->wu;
@@ -1737,6 +1742,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (tid == 0) tp2 = gtime_ns();
   int nb = 0;
   for (int b = 0; b < maxpicks; ++b) {
     // block arg-max: thread-local, warp butterfly, ONE barrier, every warp reduces the 8 warp winners
@@ -1803,6 +1809,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
       }
     }
   }
+  if (tid == 0) tp3 = gtime_ns();
   // best surviving candidate score -> upper bound of every score after the pass
   Best me{sc[0], idx[0]};
 #pragma unroll
@@ -1835,6 +1842,11 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     ctl->stat_cand_sum += v.total;
     ctl->first_round = 0;
     send->count = 0;
+    tp0 = gtime_ns();
+    ctl->stat_ns_planph[0] += tp1 - tp_begin;
+    ctl->stat_ns_planph[1] += tp2 - tp1;
+    ctl->stat_ns_planph[2] += tp3 - tp2;
+    ctl->stat_ns_planph[3] += tp0 - tp3;
   }
 }
 
@@ -2514,6 +2526,11 @@ extern "C" int vatlq_coreset_select(const float* X, int64_t n, int d, int64_t ro
     host_stats[8] = (int64_t)hc->stat_ns_wait;
     host_stats[9] = (int64_t)hc->stat_ns_tiles;
     host_stats[10] = (int64_t)hc->stat_ns_plan;
+    if (getenv("VATLQ_PASS_PHASES"))
+      fprintf(stderr, "[vatlq] planner phases, us per round: theta %.1f, records + staging %.1f, pick loop %.1f, tail %.1f (%lld rounds)\n",
+              hc->stat_ns_planph[0] / 1e3 / std::max<long long>(1, hc->stat_rounds), hc->stat_ns_planph[1] / 1e3 / std::max<long long>(1, hc->stat_rounds),
+              hc->stat_ns_planph[2] / 1e3 / std::max<long long>(1, hc->stat_rounds), hc->stat_ns_planph[3] / 1e3 / std::max<long long>(1, hc->stat_rounds),
+              (long long)hc->stat_rounds);
     if (getenv("VATLQ_PASS_PHASES"))
       fprintf(stderr, "[vatlq] pass phases as seen by CTA 0, us per launch: prologue %.1f, tiles %.1f, finishing %.1f, publish %.1f (%lld launches)\n",
               hc->stat_ns_pass[0] / 1e3 / std::max<long long>(1, hc->stat_passes), hc->stat_ns_pass[1] / 1e3 / std::max<long long>(1, hc->stat_passes),

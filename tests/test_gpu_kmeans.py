@@ -72,6 +72,27 @@ def test_kmeans_matches_sklearn(built_lib, n, d, k, weighted):
     assert np.allclose(res.centers.cpu().numpy(), km.cluster_centers_, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("n,nw,k", [(100, 30, 40), (200, 50, 60), (120, 100, 110)])
+def test_kmeans_empty_cluster_relocation(built_lib, n, nw, k):
+    """More clusters than rows that weigh anything: sklearn re-seeds the empty clusters from the farthest rows
+    (_relocate_empty_clusters_dense) and leaves those that stay empty at the biggest cluster's row
+    (_average_centers).  The reference's usage never gets here (its weights are >= 1), the estimator does: labels and
+    iteration counts against sklearn."""
+    from sklearn.cluster import KMeans
+    from vatlq import kmeans as KM
+    rng = np.random.default_rng(5 + n)
+    X = np.abs(rng.normal(0, 1, (n, 16))).astype(np.float32)
+    w = np.zeros(n)
+    w[rng.choice(n, nw, replace=False)] = 1 + rng.random(nw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        km = KMeans(n_clusters=k, random_state=318)
+        lab = km.fit_predict(X.astype(np.float64), sample_weight=w)
+    res = KM.kmeans_fit_select(torch.from_numpy(X).cuda(), k, sample_weight=torch.from_numpy(w).cuda(), select=False)
+    assert res.relocations > 0
+    assert np.array_equal(res.labels.cpu().numpy(), lab) and res.n_iter == km.n_iter_
+
+
 def test_kmeans_kernels_against_numpy(built_lib):
     """The pieces on their own: numpy-ordered column means and squared distances (bit-equal), seeding distances,
     assignment (first minimum), ragged shapes (n not a multiple of the tile, d % 32 != 0)."""

@@ -1662,6 +1662,29 @@ __device__ void choose_theta(const unsigned int* __restrict__ hist, double U, do
 constexpr int kPlanThreads = 256;
 constexpr int kPerThread = kCap / kPlanThreads;   // candidates per planner thread (strided: c = tid + 256 j)
 
+// order-preserving 64-bit key of a (non-NaN) score: key(a) > key(b) <=> a > b; -0.0 and +0.0 share a key
+__device__ __forceinline__ unsigned long long score_key(double s) {
+  if (s == 0.0) s = 0.0;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double key_score(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k));
+}
+// warp arg-max of (key, idx, pos): largest key, lowest idx on equal keys; every lane ends with the winner.
+// idx < 2^32 - 1 (0xffffffff marks "no candidate")
+__device__ __forceinline__ void warp_argmax_key(unsigned long long& key, unsigned& idx, int& pos) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  const bool top = hi == mh && lo == ml;
+  const unsigned mi = __reduce_min_sync(0xffffffffu, top ? idx : 0xffffffffu);
+  const unsigned holders = __ballot_sync(0xffffffffu, top && idx == mi);
+  pos = __shfl_sync(0xffffffffu, pos, __ffs(holders) - 1);
+  key = ((unsigned long long)mh << 32) | ml;
+  idx = mi;
+}
+
 // s_D (optional, s_D_cap doubles of shared memory): the candidate x candidate distances of as many centre rows as
 // fit are staged there with cp.async while the list is read, so that a pick's row costs a shared-memory read instead
 // of an L2 round trip on the sequential pick chain (a list of <= 163 candidates fits whole in 208 KB)
@@ -1669,6 +1692,8 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
                           long long* out_idx, Ctl* ctl, double* s_D, int s_D_cap) {
   __shared__ Best s_b[2][8];
   __shared__ int s_pos[2][8];
+  __shared__ unsigned long long s_key[2][8];
+  __shared__ unsigned int s_idx[2][8];
   __shared__ double s_theta;
   __shared__ int s_mode;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1701,7 +1726,8 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
   const CandView v = view_of(blocks, world);
   const int rule = ctl->rule;
   const double wd = ctl->wd, wu = ctl->wu;
-  const long long remaining = ctl->k - ctl->n_picked;
+  const long long picked0 = ctl->n_picked;      // (constant until the tail: read ONCE — a load per pick would stall warp 0,
+  const long long remaining = ctl->k - picked0; //  and with it every barrier of the pick chain, for an L2 round trip)
   const int maxpicks = (int)min((long long)(ctl->first_round ? 1 : min(kMaxPicks, ctl->maxb)), remaining);
   __syncthreads();   // every thread has read the block headers / ctl before thread 0 may change them
   if (v.fallback) {
@@ -1745,45 +1771,34 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
   if (tid == 0) tp2 = gtime_ns();
   int nb = 0;
   for (int b = 0; b < maxpicks; ++b) {
-    // block arg-max: thread-local, warp butterfly, ONE barrier, every warp reduces the 8 warp winners
-    Best me{sc[0], idx[0]};
+    // block arg-max on order-preserving integer keys (largest score, lowest row index on ties = better()): thread-local,
+    // three redux.sync per warp, ONE barrier, every warp reduces the 8 warp winners the same way.  (The butterfly over
+    // (fp64 score, int64 index) pairs it replaces spent ~0.8 us per pick in dependent fp64 compares and 64-bit shuffles.)
+    unsigned long long mk = score_key(sc[0]);
+    unsigned mi = (unsigned)idx[0];
     int pos = tid;
 #pragma unroll
-    for (int j = 1; j < kPerThread; ++j)
-      if (better(sc[j], idx[j], me.s, me.i)) {
-        me.s = sc[j];
-        me.i = idx[j];
+    for (int j = 1; j < kPerThread; ++j) {
+      const unsigned long long kj = score_key(sc[j]);
+      const unsigned ij = (unsigned)idx[j];
+      if (kj > mk || (kj == mk && ij < mi)) {
+        mk = kj;
+        mi = ij;
         pos = tid + kPlanThreads * j;
       }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const double s2 = __shfl_xor_sync(0xffffffffu, me.s, o);
-      const long long i2 = __shfl_xor_sync(0xffffffffu, me.i, o);
-      const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
-      if (better(s2, i2, me.s, me.i)) {
-        me.s = s2;
-        me.i = i2;
-        pos = p2;
-      }
     }
+    warp_argmax_key(mk, mi, pos);
     if (lane == 0) {
-      s_b[b & 1][warp] = me;
+      s_key[b & 1][warp] = mk;
+      s_idx[b & 1][warp] = mi;
       s_pos[b & 1][warp] = pos;
     }
     __syncthreads();
-    Best win = s_b[b & 1][lane & 7];
-    int wpos = s_pos[b & 1][lane & 7];
-#pragma unroll
-    for (int o = 4; o; o >>= 1) {
-      const double s2 = __shfl_xor_sync(0xffffffffu, win.s, o);
-      const long long i2 = __shfl_xor_sync(0xffffffffu, win.i, o);
-      const int p2 = __shfl_xor_sync(0xffffffffu, wpos, o);
-      if (better(s2, i2, win.s, win.i)) {
-        win.s = s2;
-        win.i = i2;
-        wpos = p2;
-      }
-    }
+    unsigned long long wk = lane < 8 ? s_key[b & 1][lane] : 0ULL;
+    unsigned wi = lane < 8 ? s_idx[b & 1][lane] : 0xffffffffu;
+    int wpos = lane < 8 ? s_pos[b & 1][lane] : 0;
+    warp_argmax_key(wk, wi, wpos);
+    Best win{key_score(wk), wi == 0xffffffffu ? 0x7fffffffffffffffLL : (long long)wi};
     if (!(win.s >= v.theta)) {  // a non-candidate (score < theta) could be ahead now
       if (b == 0) {             // (only possible when the rank that set theta listed nothing)
         if (tid == 0) fallback_pick(blocks, world, 1, send, out_idx, ctl);
@@ -1793,7 +1808,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     }
     if (tid == 0) {
       ctl->picks[nb] = win.i;
-      out_idx[ctl->n_picked + nb] = win.i;
+      out_idx[picked0 + nb] = win.i;
     }
     nb += 1;
     const double* drow = Dcc + (size_t)wpos * kCap;   // drow[c] = d(row c, centre = the winner), coalesced
@@ -1837,7 +1852,7 @@ __device__ void plan_body(const RankBlock* blocks, RankBlock* send, const double
     ctl->U = fmax(bb.s, v.theta);
     ctl->W = W;
     ctl->nb = nb;          // nb >= 1: the first winner is the global argmax (score >= theta)
-    ctl->n_picked += nb;
+    ctl->n_picked = picked0 + nb;
     ctl->stat_rounds += 1;
     ctl->stat_cand_sum += v.total;
     ctl->first_round = 0;
@@ -2011,6 +2026,7 @@ static Geom geom_of(int d) {
 static int check_x(const float* X, int64_t n, int d, int64_t lo, int64_t hi) {
   VQ_REQUIRE(X != nullptr && ((uintptr_t)X & 15) == 0, "X must be a 16-byte aligned device pointer");
   VQ_REQUIRE(n > 0 && d > 0 && (d & 3) == 0, "d must be a positive multiple of 4");
+  VQ_REQUIRE(n < 0xffffffffLL, "n must be below 2^32 - 1 (the planner reduces 32-bit row ids)");
   VQ_REQUIRE(0 <= lo && lo <= hi && hi <= n, "bad row range");
   VQ_REQUIRE(pass_smem_bytes(geom_of(d).S) <= (size_t)kMaxSmem, "d too large (centers must fit shared memory)");
   return 0;

@@ -43,12 +43,14 @@ def _f64(*shape, dev):
 
 
 def kmeans_fit_select(X: torch.Tensor, n_clusters: int, sample_weight: torch.Tensor | None = None, random_state: int = 318,
-                      max_iter: int = 300, tol: float = 1e-4, group=None) -> KMeansResult:
+                      max_iter: int = 300, tol: float = 1e-4, group=None, select: bool = True) -> KMeansResult:
     """`KMeans(n_clusters, random_state=random_state).fit_predict(X, sample_weight)` (k-means++ init, n_init = 1,
     Lloyd) + the per-cluster closest member.  X (n,d) fp32 CUDA, sample_weight (n,) fp64 CUDA or None.
     group: a torch.distributed group whose ranks all hold the SAME X: the assignment GEMM (the dominant step of a
     Lloyd iteration) is sharded by rows and the labels are all-gathered; seeding and the M step replay identically
-    on every rank (deterministic kernels), so every rank returns the same result as a single GPU."""
+    on every rank (deterministic kernels), so every rank returns the same result as a single GPU.
+    select=False: the clustering alone (`fit_predict`); query_rows holds -1 for clusters without members instead of
+    raising like the reference's per-cluster arg-min does."""
     X = _cuda(X, torch.float32, "X")
     if X.dim() != 2:
         raise _lib.VatlqError("X must be (n,d)")
@@ -162,6 +164,8 @@ def kmeans_fit_select(X: torch.Tensor, n_clusters: int, sample_weight: torch.Ten
         picks = _i32(k, dev)
         _lib.check(L.vatlq_kmeans_pick(_ptr(dis), _ptr(order), _ptr(starts), k, _ptr(picks), st), "vatlq_kmeans_pick")
         picks_h = picks[:k].cpu().numpy()
+    if not select:
+        return KMeansResult([int(v) for v in picks_h], labels[:n], centers, n_iter, center_ids[:k], relocations)
     cluster_num = int((picks_h >= 0).sum())                         # len(np.unique(cluster_idxs))
     rows = []
     for i in range(cluster_num):                                    # `for i in range(cluster_num)` of the reference

@@ -138,7 +138,9 @@ __device__ void push_block(const PushArgs& p, const RankBlock* send) {
       dst->score[q] = __ldcg(&send->score[q]);
     }
   }
-  __threadfence_system();
+  // release: the barrier orders every thread's record stores before the flag writers' system-scope fence (fences are
+  // cumulative), which orders them before the flag.  ONE fence per flag writer — a MEMBAR.SYS by all twelve warps
+  // ahead of the barrier, as in round 1, only added its latency to every multi-GPU round.
   __syncthreads();
   if (tid < p.world) {
     __threadfence_system();

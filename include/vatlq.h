@@ -234,7 +234,7 @@ int vatlq_fuse_blend(const double* unc, const double* infl, const uint8_t* mask,
  * skimage.feature.peak_local_max(map, min_distance=5, num_peaks=5) — 11x11 maximum filter with edge
  * replication, pixel > map minimum, 5-pixel border excluded, greedy spacing in descending value —
  * MPE = sum_j entropy(softmax(peaks_j)), Margin = sum_j |peak_0 - peak_1| (fp32).  Either output may be NULL.
- * ws >= vatlq_peak_workspace_bytes(n, J, h, w).  64 x 48 maps take a register-window fast path; maps whose
+ * ws >= vatlq_peak_workspace_bytes(n, J, h, w).  64 x 48 maps take a register / warp-shuffle fast path; maps whose
  * peak-candidate list overflows (plateaus) are redone by the generic routine — same result either way.
  * (scikit-image is absent from the build container: parity with the library itself is
  * pinned only against a restatement of its published algorithm, oracle/vatl_oracle.py.) */

@@ -254,6 +254,50 @@ __device__ __forceinline__ void window11(float (&p)[N]) {   // p[i] <- max(p[i .
   for (int i = 0; i < N - 10; ++i) p[i] = fmaxf(p[i], p[i + 3]);     // width 11
 }
 
+// the <= 5 peaks of a map from its candidate list (mask pixels: value, row-major index): five rounds of "best remaining
+// candidate (largest value, lowest index on ties), then drop everything within Chebyshev distance < 5 of it"; one warp
+__device__ __forceinline__ void peak_select(const float* cval, const int* cidx, int ncand, int lane, float* mpe_out, float* margin_out) {
+  float v8[kPfCand / 32];
+  int i8[kPfCand / 32];
+#pragma unroll
+  for (int j = 0; j < kPfCand / 32; ++j) {
+    const int q = lane + 32 * j;
+    v8[j] = q < ncand ? cval[q] : -INFINITY;
+    i8[j] = q < ncand ? cidx[q] : 0x7fffffff;
+  }
+  float peaks[5];
+  int npk = 0;
+  for (int r = 0; r < 5; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kPfCand / 32; ++j)
+      if (i8[j] != 0x7fffffff && (v8[j] > bv || (v8[j] == bv && i8[j] < bi))) {
+        bv = v8[j];
+        bi = i8[j];
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (i2 != 0x7fffffff && (bi == 0x7fffffff || v2 > bv || (v2 == bv && i2 < bi))) {
+        bv = v2;
+        bi = i2;
+      }
+    }
+    if (bi == 0x7fffffff) break;
+    peaks[npk++] = bv;
+    const int py = bi / kPfW, px = bi - py * kPfW;
+#pragma unroll
+    for (int j = 0; j < kPfCand / 32; ++j)
+      if (i8[j] != 0x7fffffff) {
+        const int yy = i8[j] / kPfW, xx = i8[j] - yy * kPfW;
+        if (abs(yy - py) < kPeakMinDist && abs(xx - px) < kPeakMinDist) i8[j] = 0x7fffffff;
+      }
+  }
+  if (lane == 0) peak_scores(peaks, npk, mpe_out, margin_out);
+}
+
 __global__ void __launch_bounds__(kPfWarps * 32, 1)
 peak_unc_fast_kernel(const float* __restrict__ H, long long maps, float* __restrict__ mpe_map, float* __restrict__ margin_map,
                      unsigned int* __restrict__ redo_count, int* __restrict__ redo_list) {
@@ -345,46 +389,103 @@ peak_unc_fast_kernel(const float* __restrict__ H, long long maps, float* __restr
     if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int)mi;
     return;
   }
-  // candidates lane + 32 j in registers
-  float v8[kPfCand / 32];
-  int i8[kPfCand / 32];
+  peak_select(cval, cidx, ncand, lane, mpe_map + mi, margin_map + mi);
+}
+
+// ---- 64 x 48 register path (the default).  No staging of the map at all: lane l reads rows 2l and 2l+1 straight from
+// global memory (96 contiguous floats), gets their 11-wide row maxima by doubling in registers, and the 11-tall column
+// maxima from its neighbours' row maxima with six shuffles per column: rows 2l-4 .. 2l+5 are the row pairs of lanes
+// l-2 .. l+2 (pair maximum m), row 2l-5 is the second row of lane l-3, row 2l+6 the first row of lane l+3.  Source
+// lanes are clamped to 0 .. 31: a clamped lane only repeats rows that are inside the window already, which is exactly
+// what edge replication does to a maximum.  The originals are read a second time (L1 / L2) for the mask test.
+// Shared memory: the candidate list only -> occupancy is set by registers (12 warps per SM instead of 7).
+constexpr int kPrWarps = 4;
+__global__ void __launch_bounds__(kPrWarps * 32, 3)
+peak_unc_reg_kernel(const float* __restrict__ H, long long maps, float* __restrict__ mpe_map, float* __restrict__ margin_map,
+                    unsigned int* __restrict__ redo_count, int* __restrict__ redo_list) {
+  __shared__ float s_cval[kPrWarps][kPfCand];
+  __shared__ int s_cidx[kPrWarps][kPfCand];
+  __shared__ int s_cnt[kPrWarps];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long mi = (long long)blockIdx.x * kPrWarps + wp;
+  if (mi >= maps) return;
+  float* cval = s_cval[wp];
+  int* cidx = s_cidx[wp];
+  int* ccount = &s_cnt[wp];
+  if (lane == 0) *ccount = 0;
+  const float4* src = reinterpret_cast<const float4*>(H + (size_t)mi * (kPfH * kPfW) + (size_t)lane * (2 * kPfW));
+  float a[kPfW], b[kPfW];           // row maxima of rows 2l / 2l+1, then their window maxima
+  float vmin = INFINITY;
 #pragma unroll
-  for (int j = 0; j < kPfCand / 32; ++j) {
-    const int q = lane + 32 * j;
-    v8[j] = q < ncand ? cval[q] : -INFINITY;
-    i8[j] = q < ncand ? cidx[q] : 0x7fffffff;
+  for (int rr = 0; rr < 2; ++rr) {
+    float p[kPfW + 2 * kPfPad];
+#pragma unroll
+    for (int q = 0; q < kPfW / 4; ++q) {
+      const float4 v = __ldg(src + rr * (kPfW / 4) + q);
+      p[kPfPad + 4 * q] = v.x; p[kPfPad + 4 * q + 1] = v.y; p[kPfPad + 4 * q + 2] = v.z; p[kPfPad + 4 * q + 3] = v.w;
+      vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int i = 0; i < kPfPad; ++i) {
+      p[i] = p[kPfPad];
+      p[kPfPad + kPfW + i] = p[kPfPad + kPfW - 1];
+    }
+    window11(p);
+#pragma unroll
+    for (int x = 0; x < kPfW; ++x) {
+      if (rr == 0) a[x] = p[x];
+      else b[x] = p[x];
+    }
   }
-  float peaks[5];
-  int npk = 0;
-  for (int r = 0; r < 5; ++r) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < kPfCand / 32; ++j)
-      if (i8[j] != 0x7fffffff && (v8[j] > bv || (v8[j] == bv && i8[j] < bi))) {
-        bv = v8[j];
-        bi = i8[j];
-      }
+  for (int o = 16; o; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+  const int lu1 = max(lane - 1, 0), lu2 = max(lane - 2, 0), lu3 = max(lane - 3, 0);
+  const int ld1 = min(lane + 1, 31), ld2 = min(lane + 2, 31), ld3 = min(lane + 3, 31);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (i2 != 0x7fffffff && (bi == 0x7fffffff || v2 > bv || (v2 == bv && i2 < bi))) {
-        bv = v2;
-        bi = i2;
+  for (int x = 0; x < kPfW; ++x) {
+    const float m = fmaxf(a[x], b[x]);
+    const float u1 = __shfl_sync(0xffffffffu, m, lu1), u2 = __shfl_sync(0xffffffffu, m, lu2);
+    const float d1 = __shfl_sync(0xffffffffu, m, ld1), d2 = __shfl_sync(0xffffffffu, m, ld2);
+    const float eu = __shfl_sync(0xffffffffu, b[x], lu3), ed = __shfl_sync(0xffffffffu, a[x], ld3);
+    const float m5 = fmaxf(fmaxf(m, fmaxf(u1, u2)), fmaxf(d1, d2));
+    a[x] = fmaxf(m5, eu);
+    b[x] = fmaxf(m5, ed);
+  }
+  __syncwarp();
+  int n_eq = 0;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int y = 2 * lane + rr;
+    const bool yin = y >= kPfPad && y < kPfH - kPfPad;
+#pragma unroll
+    for (int q = 0; q < kPfW / 4; ++q) {
+      const float4 v4 = __ldg(src + rr * (kPfW / 4) + q);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int x = 4 * q + e;
+        const float wm = rr == 0 ? a[x] : b[x];
+        const bool eq = vv[e] == wm;
+        n_eq += eq ? 1 : 0;
+        if (eq && yin && x >= kPfPad && x < kPfW - kPfPad && vv[e] > vmin) {
+          const int pos = atomicAdd(ccount, 1);
+          if (pos < kPfCand) {
+            cval[pos] = vv[e];
+            cidx[pos] = y * kPfW + x;
+          }
+        }
       }
     }
-    if (bi == 0x7fffffff) break;
-    peaks[npk++] = bv;
-    const int py = bi / kPfW, px = bi - py * kPfW;
-#pragma unroll
-    for (int j = 0; j < kPfCand / 32; ++j)
-      if (i8[j] != 0x7fffffff) {
-        const int yy = i8[j] / kPfW, xx = i8[j] - yy * kPfW;
-        if (abs(yy - py) < kPeakMinDist && abs(xx - px) < kPeakMinDist) i8[j] = 0x7fffffff;
-      }
   }
-  if (lane == 0) peak_scores(peaks, npk, mpe_map + mi, margin_map + mi);
+  n_eq = warp_sum(n_eq);
+  __syncwarp();
+  int ncand = *ccount;
+  if (n_eq == kPfH * kPfW) ncand = 0;                       // trivial image: no peak at all
+  if (ncand > kPfCand) {                                     // large plateaus: the generic kernel redoes this map
+    if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int)mi;
+    return;
+  }
+  peak_select(cval, cidx, ncand, lane, mpe_map + mi, margin_map + mi);
 }
 
 // per-frame sums over the joints, in joint order
@@ -542,8 +643,12 @@ extern "C" int vatlq_peak_unc(const float* H, int64_t n, int J, int h, int w, fl
     unsigned int* redo_count = (unsigned int*)((char*)ws + (size_t)maps * 8);
     int* redo_list = (int*)((char*)ws + (size_t)maps * 8 + 16);
     VQ_CUDA(cudaMemsetAsync(redo_count, 0, 16, stream));
-    peak_unc_fast_kernel<<<(unsigned)((maps + kPfWarps - 1) / kPfWarps), kPfWarps * 32, kPfWarps * kPfSmemWarp, stream>>>(
-        H, maps, mm, mm + maps, redo_count, redo_list);
+    if (getenv("VATLQ_PEAK_SMEM") != nullptr)      // the shared-memory-staged variant (measurement switch)
+      peak_unc_fast_kernel<<<(unsigned)((maps + kPfWarps - 1) / kPfWarps), kPfWarps * 32, kPfWarps * kPfSmemWarp, stream>>>(
+          H, maps, mm, mm + maps, redo_count, redo_list);
+    else
+      peak_unc_reg_kernel<<<(unsigned)((maps + kPrWarps - 1) / kPrWarps), kPrWarps * 32, 0, stream>>>(H, maps, mm, mm + maps, redo_count,
+                                                                                               redo_list);
     VQ_LAUNCHED();
     const unsigned rgrid = (unsigned)std::min<long long>((maps + kPeakWarps - 1) / kPeakWarps, (long long)sm_count() * 4);
     peak_unc_redo_kernel<<<rgrid, kPeakWarps * 32, (size_t)kPeakWarps * 2 * kPfH * kPfW * sizeof(float), stream>>>(

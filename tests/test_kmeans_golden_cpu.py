@@ -53,3 +53,41 @@ def test_random_stream_matches_sklearn_seeding():
         pot, closest = D[b].sum(), D[b]
         ids.append(int(cand[b]))
     assert ids == idx_ref.tolist()
+
+
+def test_device_algorithm_restated_in_numpy_equals_sklearn():
+    """oracle/kmeans_restated.py is the device pipeline (kmeans.cu + kmeans.py) step for step in NumPy: k-means++ on the
+    host's random block, Lloyd with centred-frame centre sums, relocation of empty clusters, numpy-ordered final
+    distances.  It must give sklearn's labels, iteration counts and the reference's queried rows — on the golden
+    pools, on pools with many two-member clusters (rounding-level ties), with weights, and with empty clusters."""
+    from sklearn.cluster import KMeans
+    from oracle import kmeans_restated as KR
+    from oracle import vatl_oracle as O
+    z = np.load(os.path.join(ROOT, "tests", "golden", "kmeans.npz"))
+    for tag in ("clustered", "pairs", "one", "all", "dups"):
+        X, cand, score, k, w_unc, cw = case_inputs(z, tag)
+        rows, labels, n_iter, _, _ = KR.fit_select(X[cand], k)
+        assert [cand[i] for i in rows] == z[f"{tag}_km_query"].tolist()
+        assert np.array_equal(labels, z[f"{tag}_km_labels"]) and n_iter == int(z[f"{tag}_km_niter"])
+    rng = np.random.default_rng(7)
+    for n, d, k, weighted in ((300, 64, 250, False), (400, 32, 60, True), (120, 256, 100, True)):
+        X = np.abs(rng.normal(0, 1, (n, d))).astype(np.float32)
+        w = (1 + rng.random(n)) if weighted else None
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            km = KMeans(n_clusters=k, random_state=318)
+            lab = km.fit_predict(X.astype(np.float64), sample_weight=w)
+            ref_rows = O._closest_member_per_cluster(X.astype(np.float64), km, lab)
+        rows, labels, n_iter, _, _ = KR.fit_select(X, k, w)
+        assert np.array_equal(labels, lab) and n_iter == km.n_iter_ and rows == ref_rows
+    # more clusters than rows that weigh anything: relocation + clusters that stay empty
+    X = np.abs(rng.normal(0, 1, (100, 16))).astype(np.float32)
+    w = np.zeros(100)
+    w[rng.choice(100, 30, replace=False)] = 1 + rng.random(30)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        km = KMeans(n_clusters=40, random_state=318)
+        lab = km.fit_predict(X.astype(np.float64), sample_weight=w)
+    ids = KR.seeds(X.astype(np.float64), w, 40, np.random.RandomState(318))
+    labels, _, n_iter, reloc = KR.lloyd(X.astype(np.float64), w, ids, np.var(X.astype(np.float64), axis=0).mean() * 1e-4)
+    assert reloc > 0 and np.array_equal(labels, lab) and n_iter == km.n_iter_

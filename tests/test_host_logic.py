@@ -184,3 +184,58 @@ def test_synthetic_generators_are_seeded():
     assert a.shape == (3, 17, 64, 48) and a.dtype == np.float32 and np.array_equal(a, b)
     assert (a < 0).any()
     assert synth.embeddings(40, 64).shape == (40, 64)
+
+
+def test_forward_with_embedding_runs_the_backbone_once():
+    """Producer side of SURVEY 8f-4: estimators shaped like the reference's (forward and get_embedding both start with
+    self.preact, fastpose.py:44-73) give heat maps AND embedding from one backbone pass; the result equals the
+    reference's two calls; other estimators keep the two calls."""
+    import torch
+    from vatlq import active_learning as AL
+
+    class Pose(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.preact = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU())
+            self.avgpool = torch.nn.AdaptiveAvgPool2d(1)
+            self.head = torch.nn.Conv2d(8, 17, 1)
+            self.calls = 0
+            self.preact.register_forward_hook(lambda *a: setattr(self, "calls", self.calls + 1))
+
+        def forward(self, x):
+            return self.head(self.preact(x))
+
+        def get_embedding(self, x):
+            return torch.flatten(self.avgpool(self.preact(x)), 1)
+
+    torch.manual_seed(0)
+    m = Pose().eval()
+    x = torch.randn(5, 3, 16, 12)
+    with torch.no_grad():
+        out, emb = AL.forward_with_embedding(m, x, True)
+        assert m.calls == 1 and len(m.preact._forward_hooks) == 1          # one backbone pass; the temporary hook is gone
+        assert torch.equal(out, m(x)) and torch.equal(emb, m.get_embedding(x))
+        m.calls = 0
+        out2, emb2 = AL.forward_with_embedding(m, x, True, fuse=False)
+        assert m.calls == 2 and torch.equal(out2, out) and torch.equal(emb2, emb)
+        m.calls = 0
+        out3, none = AL.forward_with_embedding(m, x, False)
+        assert m.calls == 1 and none is None and torch.equal(out3, out)
+        class Wrap(torch.nn.Module):            # `.module` unwrapping (torch.nn.DataParallel on one device)
+            def __init__(self, inner):
+                super().__init__()
+                self.module = inner
+            def forward(self, x):
+                return self.module(x)
+        m.calls = 0
+        out4, emb4 = AL.forward_with_embedding(Wrap(m), x, True)
+        assert m.calls == 1 and torch.equal(out4, out) and torch.equal(emb4, emb)
+
+    class Plain(torch.nn.Module):           # no preact: the reference's two calls
+        def forward(self, x):
+            return x[:, :1] * 2
+        def get_embedding(self, x):
+            return x.flatten(1)[:, :4]
+    p = Plain()
+    o, e = AL.forward_with_embedding(p, x, True)
+    assert torch.equal(o, x[:, :1] * 2) and torch.equal(e, x.flatten(1)[:, :4])

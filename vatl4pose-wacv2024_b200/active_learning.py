@@ -119,6 +119,29 @@ class WholeBodyAE(nn.Module):
         return ops.wpu(_as_cuda(kpts).reshape(-1, ops.J, 3), _as_cuda(boxes_xyxy).reshape(-1, 4), w, ind, z, drop_ears)
 
 
+def forward_with_embedding(model, crops, want_embedding: bool, fuse: bool = True):
+    """The estimator's heat maps and, when wanted, its 2048-d embedding for one batch (ActiveLearning.py:277-286).
+    The reference runs the backbone twice: `self.model(inps)` and `self.model.module.get_embedding(inps)`, both of
+    which start with `self.preact(x)` (alphapose/models/fastpose.py:44-59,70-73, simplepose.py:82-91).  When the
+    estimator has that shape (`preact` + `avgpool`), a forward hook keeps the backbone output of the ONE forward and
+    the embedding is `flatten(avgpool(out), 1)` of it — `get_embedding`'s own two lines — so the backbone runs once
+    (producer side).  The estimator itself is untouched; anything else (no `preact`, several replicas
+    under DataParallel, fuse=False / `opt.fuse_embedding = False`) takes the reference's two calls."""
+    core = model.module if hasattr(model, "module") else model
+    if want_embedding and fuse and hasattr(core, "preact") and hasattr(core, "avgpool"):
+        grabbed = []
+        handle = core.preact.register_forward_hook(lambda mod, inp, out: grabbed.append(out))
+        try:
+            out = model(crops)
+        finally:
+            handle.remove()
+        if len(grabbed) == 1 and torch.is_tensor(grabbed[0]):
+            return out, torch.flatten(core.avgpool(grabbed[0]), 1)
+        return out, core.get_embedding(crops)          # replicas / an unexpected call pattern: the reference's second call
+    out = model(crops)
+    return out, (core.get_embedding(crops) if want_embedding else None)
+
+
 class IndexCollection:
     """The part of alipy.index.IndexCollection (ALiPy/alipy/index/index_collections.py:26-226)
     the query path uses: an ordered, duplicate-free list of ints with set-speed membership."""
@@ -340,9 +363,9 @@ class ActiveLearning:
             if not torch.equal(idx_t, torch.arange(pos, pos + b)):
                 raise _lib.VatlqError("eval_loader must walk the id-sorted pool in order (shuffle=False)")
             cur = inps[:, 0].to(dev)
-            H = m(cur)[:, self.eval_joints].float().contiguous()          # (:277-281)
+            out, emb = forward_with_embedding(m, cur, want_feat, fuse=bool(getattr(self.opt, "fuse_embedding", True)))
+            H = out[:, self.eval_joints].float().contiguous()             # (:277-281)
             if want_feat:
-                emb = m.module.get_embedding(cur) if hasattr(m, "module") else m.get_embedding(cur)
                 X[pos:pos + b] = emb.float()                              # (:283-286)
             boxes = torch.as_tensor(np.asarray(bboxes_crop), dtype=torch.float32).reshape(b, 4).to(dev)
             ip = torch.as_tensor(np.asarray(isPrev)).to(torch.uint8)

@@ -62,3 +62,56 @@ def test_halo_and_gather_world2():
         for p in ps:
             p.join(timeout=60)
         assert sorted(res) == [(0, True), (1, True)], res
+
+
+def _kmeans_worker(rank, world, port, q):
+    """kmeans.py with group=WORLD on two CPU processes: the assignment step is sharded by rows, labels all-gathered, the
+    change count summed; the device calls are the NumPy stand-ins of tests/test_kmeans_host_cpu.py."""
+    import contextlib
+    import sys
+    import warnings
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [os.path.dirname(here), here]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vatlq  # noqa: F401
+        from vatlq import _lib, kmeans as KM
+        from test_kmeans_host_cpu import FakeLib
+        from sklearn.cluster import KMeans
+        fake = FakeLib()
+        _lib.lib = lambda: fake
+        KM._cuda = lambda t, dt, name: t.contiguous()
+        KM._stream = lambda: None
+        torch.cuda.device = lambda dev: contextlib.nullcontext()
+        rng = np.random.default_rng(4)                       # identical pool on every rank
+        n, d, k = 301, 20, 23                                # ragged shards
+        X = np.abs(rng.normal(0, 1, (n, d))).astype(np.float32)
+        w = 1 + rng.random(n)
+        fake.n, fake.k = n, k
+        res = KM.kmeans_fit_select(torch.from_numpy(X), k, sample_weight=torch.from_numpy(w), group=td.group.WORLD)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            km = KMeans(n_clusters=k, random_state=318)
+            lab = km.fit_predict(X.astype(np.float64), sample_weight=w)
+        ok = bool(np.array_equal(res.labels.numpy(), lab)) and res.n_iter == km.n_iter_
+        rows = torch.tensor(res.query_rows)
+        both = [torch.empty_like(rows) for _ in range(world)]
+        td.all_gather(both, rows)
+        ok &= all(torch.equal(b, rows) for b in both)        # every rank returns the same picks
+        q.put((rank, ok))
+    finally:
+        td.destroy_process_group()
+
+
+def test_kmeans_row_sharded_assignment_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_kmeans_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)], res

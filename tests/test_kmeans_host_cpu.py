@@ -208,3 +208,29 @@ def test_host_flow_weights_relocation_and_errors(km_on_cpu):
         km_on_cpu(Xd, 250)
     with pytest.raises(ValueError, match="should be >= n_clusters"):
         km_on_cpu(X[:5], 6)
+
+
+def test_unique_rows_first_index_equals_numpy_unique(monkeypatch):
+    """np.unique(E, axis=0, return_index=True)[1] (ActiveLearning.py:555) from a sort by the first column plus a full
+    comparison of the runs that share it: duplicates, rows that differ only in later columns, signed zeros."""
+    import vatlq  # noqa: F401
+    from vatlq import kmeans as KM
+    monkeypatch.setattr(KM, "_cuda", lambda t, dt, name: t.contiguous())
+
+    def rank_scores(score, mask=None, descending=True, count=None):        # vatlq_rank_scores: stable, ties by id
+        s = np.where(score.numpy() == 0, 0.0, score.numpy())
+        order = np.argsort(-s if descending else s, kind="stable")
+        return torch.from_numpy(order if count is None else order[:count])
+    monkeypatch.setattr(KM, "rank_scores", rank_scores)
+    rng = np.random.default_rng(2)
+    E = np.abs(rng.normal(0, 1, (200, 12))).astype(np.float32)
+    E[50:80] = E[10:40]                           # duplicates
+    E[100:110, 0] = E[5, 0]                       # same first column, different rows
+    E[120:125, :3] = E[6, :3]                     # same first three columns
+    E[130, 0] = 0.0
+    E[131, 0] = -0.0                              # signed zeros compare equal
+    E[131, 1:] = E[130, 1:]
+    got = KM.unique_rows_first_index(torch.from_numpy(E))
+    _, ref = np.unique(E.astype(np.float64), axis=0, return_index=True)
+    assert np.array_equal(got, ref)
+    assert KM.unique_rows_first_index(torch.zeros((0, 4))).size == 0

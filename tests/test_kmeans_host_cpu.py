@@ -234,3 +234,46 @@ def test_unique_rows_first_index_equals_numpy_unique(monkeypatch):
     _, ref = np.unique(E.astype(np.float64), axis=0, return_index=True)
     assert np.array_equal(got, ref)
     assert KM.unique_rows_first_index(torch.zeros((0, 4))).size == 0
+
+
+@pytest.mark.parametrize("flt", ["K-Means", "weighted"])
+def test_controller_kmeans_filters_host_logic(km_on_cpu, monkeypatch, flt):
+    """ActiveLearning._kmeans_query (candidate list, np.unique de-duplication, weights 1 + w_unc * cw * score, query-size
+    clamp, the reference's index mapping of :580) against the oracle's restatement of ActiveLearning.py:553-608."""
+    from types import SimpleNamespace
+    import vatlq
+    from vatlq import _lib, kmeans as KM
+    from oracle import vatl_oracle as O
+    synth = vatlq.synth
+
+    def rank_scores(score, mask=None, descending=True, count=None):
+        s = np.where(score.numpy() == 0, 0.0, score.numpy())
+        order = np.argsort(-s if descending else s, kind="stable")
+        return torch.from_numpy(order if count is None else order[:count])
+    monkeypatch.setattr(KM, "rank_scores", rank_scores)
+    n = 300
+    cfg = SimpleNamespace(VAL=SimpleNamespace(QUERY_RATIO=[0.05, 0.1], W_UNC=0.8, UNC_LAMBDA=0.01),
+                          DATA_PRESET=SimpleNamespace(HEATMAP_SIZE=[64, 48]), AE=SimpleNamespace(Z_DIM=4))
+    opt = SimpleNamespace(strategy=f"THC+None_{flt}filter", uncertainty="THC", representativeness="None", filter=flt,
+                          video_id="0", THCvsWPU="const", fixed_lambda=False, onebyone=False)
+    al = vatlq.ActiveLearning(cfg, opt, eval_len=n)
+    X = synth.pool_embeddings(n, kind="weak", seed=11)
+    X[50:70] = X[10:30]
+    labeled = list(range(0, n, 9))
+    al.labeled_id.update(labeled)
+    al.unlabeled_id.difference_update(labeled)
+    unl = al.unlabeled_id.index
+    score = np.zeros(n)
+    score[unl] = synth.pool_unc(n, seed=11)[unl]
+    fake = _lib.lib()
+    cand = sorted(unl)
+    m = len(cand) if flt == "K-Means" else len(np.unique(X[cand].astype(np.float64), axis=0))
+    fake.n, fake.k = m, min(al.query_size, m)
+    got = al._kmeans_query(torch.from_numpy(X), torch.from_numpy(score), unl, 0.4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if flt == "K-Means":
+            ref, qs, _ = O.kmeans_filter(X.astype(np.float64), cand, 15, len(unl))
+        else:
+            ref, qs, _, _ = O.weighted_kmeans_filter(X.astype(np.float64), cand, score[cand], 0.8, 0.4, 15, len(unl))
+    assert got == ref and al.query_size == qs
